@@ -1,0 +1,77 @@
+"""ctypes binding of libgavatar_sm100.so (the C ABI declared in include/gavatar.h).
+
+There is no CPU fallback and no alternative backend: if the library is missing or a call fails, a RuntimeError is
+raised.  The library is built in-tree by ``gaussianavatar_b200.build.build_library()`` (``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from .build import LIB_PATH
+
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_vp = ctypes.c_void_p
+
+
+class GaRasterSettings(ctypes.Structure):
+    _fields_ = [("P", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("tanfovx", ctypes.c_float), ("tanfovy", ctypes.c_float), ("scale_modifier", ctypes.c_float)]
+
+
+class GaRasterViews(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in ("depth", "xy", "conic_opacity", "cov3d", "tiles_touched", "offsets", "rect",
+                                    "keys_unsorted", "keys_sorted", "vals_unsorted", "vals_sorted", "ranges", "final_T",
+                                    "n_contrib")]
+
+
+# name -> (restype, argtypes); every symbol include/gavatar.h declares must be listed here (tests check both ways)
+_SIGNATURES = {
+    "ga_version": (ctypes.c_int, []),
+    "ga_last_error": (ctypes.c_char_p, []),
+    "ga_launch_count": (ctypes.c_longlong, []),
+    "ga_raster_geom_bytes": (ctypes.c_size_t, [ctypes.c_int32]),
+    "ga_raster_img_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
+    "ga_raster_binning_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
+    "ga_raster_bwd_scratch_bytes": (ctypes.c_size_t, [ctypes.c_int32]),
+    "ga_raster_forward_preprocess": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings)] + [c_vp] * 8 + [ctypes.POINTER(ctypes.c_int64), c_vp]),
+    "ga_raster_forward_render": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings), c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64, c_vp, c_vp, c_vp]),
+    "ga_raster_backward": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings)] + [c_vp] * 11 + [ctypes.c_int64] + [c_vp] * 9),
+    "ga_raster_views": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings), c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(GaRasterViews)]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the sm_100a CUDA library has not been built. Run "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). There is no CPU fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)     # AttributeError if the .so is stale -> loud
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().ga_last_error()
+        raise RuntimeError(f"libgavatar {what} failed (status {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def launch_count() -> int:
+    return int(lib().ga_launch_count())

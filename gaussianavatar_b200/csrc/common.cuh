@@ -1,0 +1,64 @@
+// Shared helpers for libgavatar_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/gavatar.h"
+
+namespace ga {
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define GA_CHECK_CUDA(expr)                                                                          \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            ::ga::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return GA_ERR_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+#define GA_CHECK_LAUNCH(name)                                                                        \
+    do {                                                                                             \
+        ::ga::count_launch();                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                         \
+        if (_e != cudaSuccess) {                                                                     \
+            ::ga::set_error("launch of %s failed: %s (%s:%d)", name, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return GA_ERR_CUDA;                                                                      \
+        }                                                                                            \
+    } while (0)
+
+#define GA_REQUIRE(cond, ...)                                                                        \
+    do {                                                                                             \
+        if (!(cond)) {                                                                               \
+            ::ga::set_error(__VA_ARGS__);                                                            \
+            return GA_ERR_INVALID;                                                                   \
+        }                                                                                            \
+    } while (0)
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+// Bump carving of a caller-owned byte buffer into aligned typed regions.
+struct Carver {
+    char *base;
+    size_t off;
+    explicit Carver(void *p) : base(static_cast<char *>(p)), off(0) {}
+    template <typename T> T *take(size_t n)
+    {
+        off = align_up(off);
+        T *r = reinterpret_cast<T *>(base + off);
+        off += n * sizeof(T);
+        return r;
+    }
+    size_t used() const { return align_up(off); }
+};
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+constexpr int kNumSMs = 148;  // B200
+
+}  // namespace ga
