@@ -1,0 +1,130 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by importing the UNMODIFIED reference modules from
+/root/reference (read-only, never copied).  Run in the build container only (the GPU box has no /root/reference):
+
+    python oracle/gen_golden.py
+
+Each fixture stores the reference's OUTPUTS (and small inputs); large inputs are regenerated from seeds by
+oracle.avatar_oracle.seeded_pop_params / gaussianavatar_b200.synthetic so the fixtures stay small.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+from model.network import POP_no_unet                     # noqa: E402  (reference)
+from submodules.smplx.lbs import lbs                      # noqa: E402  (reference)
+from utils.general_utils import getIdxMap_torch           # noqa: E402  (reference)
+from utils.graphics_utils import focal2fov, getProjectionMatrix, getWorld2View2   # noqa: E402  (reference)
+from utils.loss_utils import l1_loss_w, ssim              # noqa: E402  (reference)
+
+from gaussianavatar_b200 import synthetic as syn          # noqa: E402
+from oracle.avatar_oracle import seeded_pop_params        # noqa: E402
+
+
+def gen_test_pose_subset():
+    s = torch.load(os.path.join(REF, "assets/test_pose/smpl_parms.pth"))
+    c = np.load(os.path.join(REF, "assets/test_pose/cam_parms.npz"))
+    idx = np.arange(0, 480, 15)                          # 32 of the 480 shipped poses
+    np.savez_compressed(os.path.join(OUT, "test_pose_subset.npz"), beta=s["beta"].numpy(), body_pose=s["body_pose"].numpy()[idx],
+                        trans=s["trans"].numpy()[idx], frame_index=idx, intrinsic=c["intrinsic"], extrinsic=c["extrinsic"])
+
+
+def gen_smpl_A():
+    body = syn.make_body(0)
+    d = np.load(os.path.join(OUT, "test_pose_subset.npz"))
+    pose = torch.tensor(d["body_pose"][:16]); transl = torch.tensor(d["trans"][:16])
+    pose = torch.cat([pose, torch.zeros(1, 72)], 0); transl = torch.cat([transl, torch.zeros(1, 3)], 0)   # + T-pose
+    B = pose.shape[0]
+    _, _, A = lbs(body.betas.expand(B, -1), pose, body.v_template[None].expand(B, -1, -1).contiguous(), body.shapedirs,
+                  body.posedirs, body.J_regressor, body.parents, body.lbs_weights, return_affine_mat=True)
+    A = A.clone()
+    A[:, :, :3, 3] += transl.unsqueeze(dim=1)            # submodules/smplx/body_models.py:380-383
+    np.savez_compressed(os.path.join(OUT, "smpl_A.npz"), pose=pose.numpy(), transl=transl.numpy(), A=A.numpy(),
+                        rest_joints=body.rest_joints().numpy(), body_seed=0)
+
+
+def _pop_case(name, inp, S, B, seed, hsize=128, c_geom=64):
+    torch.manual_seed(0)
+    net = POP_no_unet(c_geom=c_geom, geom_layer_type="conv", nf=32, hsize=hsize, up_mode="upconv", use_dropout=False, uv_feat_dim=2)
+    p = seeded_pop_params(seed, c_geom, hsize)
+    missing = net.load_state_dict(p, strict=False)
+    assert not missing.unexpected_keys
+    assert all("running" in k or "num_batches" in k for k in missing.missing_keys), missing.missing_keys
+    net.train()                                          # the reference scripts never call .eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    geo = (torch.randn(1, c_geom, inp, inp, generator=g) * 0.01).requires_grad_(True)
+    uv = getIdxMap_torch(torch.rand(3, S, S))            # utils/general_utils.py:188
+    res, sc, shs = net.forward(pose_featmap=None, geom_featmap=geo.expand(B, -1, -1, -1).contiguous(),
+                               uv_loc=uv[None].expand(B, -1, -1).contiguous())
+    gr, gs, gc = (torch.randn(res.shape, generator=g), torch.randn(sc.shape, generator=g), torch.randn(shs.shape, generator=g))
+    loss = (res * gr).sum() + (sc * gs).sum() + (shs * gc).sum()
+    loss.backward()
+    grads = {k: v.grad.numpy() for k, v in net.named_parameters()}
+    keep = ["decoder.conv1.weight", "decoder.conv1.bias", "decoder.bn1.weight", "decoder.bn1.bias", "decoder.conv5.weight",
+            "decoder.bn5.weight", "decoder.conv8.weight", "decoder.conv8.bias", "decoder.conv8N.weight", "decoder.conv7SH.weight",
+            "decoder.bn7SH.bias", "decoder.conv6N.bias", "geom_proc_layers.conv1.weight", "geom_proc_layers.conv3.weight"]
+    out = dict(res=res.detach().numpy(), scales=sc.detach().numpy(), shs=shs.detach().numpy(), uv=uv.numpy(),
+               geo_grad_sub=geo.grad.numpy()[:, ::4, ::max(1, inp // 8), ::max(1, inp // 8)].copy(),
+               geo_grad_norm=float(geo.grad.norm()), bn1_running_mean=net.decoder.bn1.running_mean.numpy(),
+               bn1_running_var=net.decoder.bn1.running_var.numpy(), inp=inp, S=S, B=B, seed=seed, hsize=hsize, c_geom=c_geom)
+    for k in keep:
+        out["grad:" + k] = grads[k][:8, :8].copy() if k.startswith("geom_proc") else grads[k]
+    out["grad_norms"] = np.array([np.linalg.norm(grads[k]) for k in sorted(grads)])
+    out["grad_names"] = np.array(sorted(grads))
+    np.savez_compressed(os.path.join(OUT, name), **out)
+
+
+def gen_pop():
+    _pop_case("pop_s32_in16.npz", inp=16, S=32, B=2, seed=5)          # resample 16 -> 32, batch-identical inputs
+    _pop_case("pop_s32_in32.npz", inp=32, S=32, B=1, seed=6)          # feat_res == uv_res: resample skipped (network.py:65)
+    _pop_case("pop_s48_in128.npz", inp=128, S=48, B=1, seed=7)        # the real 128^2 input map, down-sampling case
+
+
+def gen_losses():
+    g = torch.Generator().manual_seed(9)
+    a = torch.rand(2, 3, 40, 52, generator=g).requires_grad_(True)
+    b = torch.rand(2, 3, 40, 52, generator=g)
+    l1 = l1_loss_w(a, b)
+    s = ssim(a, b)
+    (0.8 * l1 + 0.2 * (1 - s)).backward()
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), img=a.detach().numpy(), gt=b.numpy(), l1=l1.item(), ssim=s.item(),
+                        grad=a.grad.numpy())
+
+
+def gen_camera():
+    c = np.load(os.path.join(REF, "assets/test_pose/cam_parms.npz"))
+    out = {}
+    for side in (1024, 512):
+        K = np.array(c["intrinsic"], np.float32).reshape(3, 3).copy()
+        sc = side / 1024.0
+        K[0, 0] *= sc; K[1, 1] *= sc; K[0, 2] *= sc; K[1, 2] *= sc
+        extr = c["extrinsic"]
+        R = np.array(extr[:3, :3], np.float32).reshape(3, 3).transpose(1, 0)     # scene/dataset_mono.py:165-166
+        T = np.array([extr[:3, 3]], np.float32)
+        FovY, FovX = focal2fov(K[1, 1], side), focal2fov(K[0, 0], side)
+        wvt = torch.tensor(getWorld2View2(R, T, np.array([0.0, 0.0, 0.0]), 1.0)).transpose(0, 1)
+        # numpy-1.x semantics of the reference env: python-float / np.float32 -> float64 scalar (assignable into a tensor)
+        proj = getProjectionMatrix(znear=0.01, zfar=100.0, fovX=FovX, fovY=FovY, K=K.astype(np.float64), h=side, w=side).transpose(0, 1)
+        full = (wvt.unsqueeze(0).bmm(proj.unsqueeze(0))).squeeze(0)
+        out[f"wvt{side}"] = wvt.numpy(); out[f"full{side}"] = full.numpy(); out[f"center{side}"] = wvt.inverse()[3, :3].numpy()
+        out[f"fov{side}"] = np.array([FovX, FovY])
+    np.savez_compressed(os.path.join(OUT, "camera.npz"), **out)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_test_pose_subset()
+    gen_smpl_A()
+    gen_pop()
+    gen_losses()
+    gen_camera()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
