@@ -25,6 +25,21 @@ class GaRasterViews(ctypes.Structure):
                                     "n_contrib")]
 
 
+class GaDecoderDesc(ctypes.Structure):
+    _fields_ = [("S", ctypes.c_int32), ("feat_res", ctypes.c_int32), ("batch", ctypes.c_int32), ("c_geom", ctypes.c_int32),
+                ("hsize", ctypes.c_int32), ("bn_eps", ctypes.c_float), ("bn_momentum", ctypes.c_float)]
+
+
+class GaDecoderLayout(ctypes.Structure):
+    _fields_ = [("gconv", ctypes.c_int64 * 3), ("w", ctypes.c_int64 * 7), ("b", ctypes.c_int64 * 7), ("gamma", ctypes.c_int64 * 7),
+                ("beta", ctypes.c_int64 * 7), ("w8", ctypes.c_int64), ("b8", ctypes.c_int64), ("total", ctypes.c_int64),
+                ("bn_channels", ctypes.c_int32), ("bn_offset", ctypes.c_int32 * 7)]
+
+
+class GaDecoderViews(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in ("conv3_nhwc", "feat", "y1", "y5", "bn_mean", "bn_rstd", "d_feat")]
+
+
 # name -> (restype, argtypes); every symbol include/gavatar.h declares must be listed here (tests check both ways)
 _SIGNATURES = {
     "ga_version": (ctypes.c_int, []),
@@ -37,6 +52,15 @@ _SIGNATURES = {
     "ga_raster_forward_preprocess": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings)] + [c_vp] * 8 + [ctypes.POINTER(ctypes.c_int64), c_vp]),
     "ga_raster_forward_render": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings), c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64, c_vp, c_vp, c_vp]),
     "ga_raster_backward": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings)] + [c_vp] * 11 + [ctypes.c_int64] + [c_vp] * 9),
+    "ga_smpl_forward": (ctypes.c_int, [ctypes.c_int32] + [c_vp] * 7),
+    "ga_smpl_backward": (ctypes.c_int, [ctypes.c_int32] + [c_vp] * 8),
+    "ga_lbs_forward": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_float] + [c_vp] * 9),
+    "ga_lbs_backward": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float] + [c_vp] * 11),
+    "ga_decoder_layout": (ctypes.c_int, [ctypes.POINTER(GaDecoderDesc), ctypes.POINTER(GaDecoderLayout)]),
+    "ga_decoder_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(GaDecoderDesc)]),
+    "ga_decoder_forward": (ctypes.c_int, [ctypes.POINTER(GaDecoderDesc)] + [c_vp] * 6),
+    "ga_decoder_backward": (ctypes.c_int, [ctypes.POINTER(GaDecoderDesc)] + [c_vp] * 7),
+    "ga_decoder_views": (ctypes.c_int, [ctypes.POINTER(GaDecoderDesc), c_vp, ctypes.POINTER(GaDecoderViews)]),
     "ga_raster_views": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings), c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(GaRasterViews)]),
 }
 

@@ -1,0 +1,247 @@
+"""`AvatarModel` with the reference's public surface (/root/reference model/avatar_model.py:19-649) over the fused
+sm_100a kernels: SMPL pose -> cano2live (one kernel), feature net (once per step), fused LBS + attribute assembly,
+tile rasterizer per frame.
+
+Same methods / attributes as the reference: train_stage1, render_free_stage1, training_setup, zero_grad, step, save,
+load, stage_load, getTrainDataloader ..., `.net .pose .transl .geo_feature .model_path`.  Stage 2 (pose encoder U-Net,
+SURVEY.md §8f rank 2) is not built yet and raises NotImplementedError.
+
+Two ways to construct:
+  AvatarModel(model_parms, net_parms, opt_parms, train=True)   reference signature; reads the dataset folder contract
+                                                               of scene/dataset_mono.py:83-96 + assets/ (needs the
+                                                               licensed SMPL / UV assets the reference needs)
+  AvatarModel.from_assets(assets, frames, ...)                 tensors in memory (synthetic assets, benchmarks, tests)
+"""
+from __future__ import annotations
+
+import os
+from os.path import join
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .config import ModelParams, NetworkParams, OptimizationParams
+from .network import POP_no_unet
+from .ops import LbsAssemble, SmplCano2Live
+from .renderer import render_batch
+
+
+class _FrameSet(torch.utils.data.Dataset):
+    """In-memory stand-in for MonoDataset_train (scene/dataset_mono.py:98-257): yields the same dict keys."""
+
+    def __init__(self, frames):
+        self.frames = frames
+
+    def __len__(self):
+        return len(self.frames)
+
+    def __getitem__(self, i):
+        return self.frames[i]
+
+
+class AvatarModel:
+    def __init__(self, model_parms, net_parms, opt_parms, load_iteration=None, train=True, _assets=None, _frames=None,
+                 _pose_data=None, _transl_data=None, device="cuda"):
+        self.model_parms, self.net_parms, self.opt_parms = model_parms, net_parms, opt_parms
+        self.model_path = model_parms.model_path
+        self.loaded_iter = None
+        self.train = train
+        self.train_mode = model_parms.train_mode
+        self.gender = model_parms.smpl_gender
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("AvatarModel runs on CUDA only (no CPU fallback)")
+        self.batch_size = model_parms.batch_size if train else 1      # avatar_model.py:31-34
+        assert model_parms.smpl_type in ["smplx", "smpl"]
+        if model_parms.smpl_type != "smpl":
+            raise NotImplementedError("only smpl_type='smpl' (24 joints, the reference default) is built")
+        if model_parms.train_stage not in (0, 1):
+            raise NotImplementedError("train_stage 2 (pose-encoder U-Net) is the next scope row (SURVEY.md §8f rank 2)")
+
+        if _assets is None:
+            _assets, _frames, _pose_data, _transl_data = self._load_reference_assets(model_parms, train)
+        S = int(model_parms.query_posmap_size)
+        assert _assets["valid_idx"].numel() == S * S
+        dev = self.device
+        self.valid_idx = _assets["valid_idx"].to(dev)                                   # bool [S*S]
+        self.valid_index = torch.nonzero(self.valid_idx).reshape(-1).to(torch.int32).contiguous()   # order of the boolean mask
+        qp = _assets["query_points"].to(dev).float().contiguous()                      # [N,3]
+        self._query_points = qp
+        self.query_points = qp[None].expand(self.batch_size, -1, -1)                    # avatar_model.py:75-77
+        N = qp.shape[0]
+        self.fix_opacity = torch.ones((N, 1), device=dev)                               # avatar_model.py:80-83
+        rots = torch.zeros((N, 4), device=dev)
+        rots[:, 0] = 1
+        self.fix_rotation = rots
+        self._query_lbs = _assets["query_lbs"].to(dev).float().contiguous()            # [N,24], ONE copy for all frames
+        self.query_lbs = self._query_lbs[None].expand(self.batch_size, -1, -1)          # view only (reference materialises B copies, :86-87)
+        cano = _assets["cano_joint_mats"].to(dev).float()
+        self._inv_cano = torch.linalg.inv(cano).contiguous()                            # [24,4,4]  avatar_model.py:89
+        self.inv_mats = self._inv_cano[None].expand(self.batch_size, -1, -1, -1)
+        self._rest_joints = _assets["rest_joints"].to(dev).float().contiguous()        # J(beta): constant per subject
+        self.betas = _assets["betas"].to(dev).float()[None].expand(self.batch_size, -1) if "betas" in _assets else None
+
+        self.train_dataset = _FrameSet(_frames)
+        num_training_frames = _pose_data.shape[0]
+        self.pose = torch.nn.Embedding(num_training_frames, 72, _weight=_pose_data.clone().float(), sparse=True).to(dev)
+        self.transl = torch.nn.Embedding(num_training_frames, 3, _weight=_transl_data.clone().float(), sparse=True).to(dev)
+        self.optimizer_pose = torch.optim.SparseAdam(list(self.pose.parameters()) + list(self.transl.parameters()), 5.0e-3)
+        bg_color = [1, 1, 1] if model_parms.white_background else [0, 0, 0]
+        self.background = torch.tensor(bg_color, dtype=torch.float32, device=dev)
+        self.optimizer = None
+        self.scheduler = None
+        self.net_set(model_parms.train_stage)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    @classmethod
+    def from_assets(cls, assets, frames, pose_data, transl_data, batch_size=2, train=True, opt_parms=None, device="cuda"):
+        """assets: gaussianavatar_b200.synthetic.SyntheticAvatarAssets (or a dict with the same fields)."""
+        if not isinstance(assets, dict):
+            assets = dict(valid_idx=assets.valid_idx, query_points=assets.query_points, query_lbs=assets.query_lbs,
+                          cano_joint_mats=assets.cano_joint_mats, rest_joints=assets.rest_joints, betas=assets.body.betas[0], S=assets.S)
+        mp = ModelParams(batch_size=batch_size, query_posmap_size=int(assets["S"]))
+        return cls(mp, NetworkParams(), opt_parms or OptimizationParams(), train=train, _assets=assets, _frames=frames,
+                   _pose_data=pose_data, _transl_data=transl_data, device=device)
+
+    def _load_reference_assets(self, mp, train):
+        """Folder contract of the reference (model/avatar_model.py:41-98; scene/dataset_mono.py:83-160).  Needs the SMPL
+        model pickle for the rest joints; untested offline (the archive of README.md:41-54 is not available here)."""
+        split = "train" if train else "test"
+        S = int(mp.query_posmap_size)
+        mask = np.load(join(mp.project_path, "assets", "uv_masks", f"uv_mask{S}_with_faceid_smpl.npy")).reshape(S, S)
+        valid = torch.from_numpy(mask != -1).reshape(-1)
+        qmap = torch.from_numpy(np.load(join(mp.source_path, split, f"query_posemap_{S}_cano_smpl.npz"))[f"posmap{S}"]).reshape(-1, 3)
+        lbs = torch.from_numpy(np.load(join(mp.project_path, "assets", f"lbs_map_smpl_{S}.npy"))).reshape(S * S, 24)
+        cano = torch.load(join(mp.source_path, split, "smpl_cano_joint_mat.pth")).reshape(24, 4, 4)
+        smpl_data = torch.load(join(mp.source_path, "train", "smpl_parms.pth"))
+        beta = torch.as_tensor(smpl_data["beta"][0]).float()
+        import pickle
+        with open(join(mp.smpl_model_path, f"SMPL_{mp.smpl_gender.upper()}.pkl"), "rb") as f:
+            sm = pickle.load(f, encoding="latin1")
+        v_t = torch.as_tensor(np.asarray(sm["v_template"])).double()
+        sd = torch.as_tensor(np.asarray(sm["shapedirs"])[:, :, :10]).double()
+        Jr = torch.as_tensor(np.asarray(sm["J_regressor"].todense() if hasattr(sm["J_regressor"], "todense") else sm["J_regressor"])).double()
+        rest = (Jr @ (v_t + torch.einsum("l,mkl->mk", beta.double(), sd))).float()
+        pose = torch.as_tensor(smpl_data["body_pose"]).float()
+        transl = torch.as_tensor(smpl_data["trans"]).float()
+        assets = dict(valid_idx=valid, query_points=qmap[valid], query_lbs=lbs[valid].float(), cano_joint_mats=cano, rest_joints=rest,
+                      betas=beta, S=S)
+        return assets, [], pose, transl
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def net_set(self, mode):
+        assert mode in [0, 1, 2]
+        npm = self.net_parms
+        self.net = POP_no_unet(c_geom=npm.c_geom, geom_layer_type=npm.geom_layer_type, nf=npm.nf, hsize=npm.hsize, up_mode=npm.up_mode,
+                               use_dropout=bool(npm.use_dropout), uv_feat_dim=2).to(self.device)
+        inp = self.model_parms.inp_posmap_size
+        geo = torch.ones(1, npm.c_geom, inp, inp).normal_(mean=0., std=0.01).float().to(self.device)      # avatar_model.py:136
+        self.geo_feature = nn.Parameter(geo.requires_grad_(True))
+
+    def training_setup(self):
+        # avatar_model.py:148-162 (stage 1)
+        self.optimizer = torch.optim.Adam([{"params": self.net.parameters(), "lr": self.opt_parms.lr_net},
+                                           {"params": self.geo_feature, "lr": self.opt_parms.lr_geomfeat}])
+        self.scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, self.opt_parms.sched_milestones, gamma=0.1)
+
+    def save(self, iteration):
+        path = os.path.join(self.model_path, "net/iteration_{}".format(iteration))
+        os.makedirs(path, exist_ok=True)
+        torch.save({"net": self.net.state_dict(), "geo_feature": self.geo_feature, "pose": self.pose.state_dict(),
+                    "transl": self.transl.state_dict(), "optimizer": self.optimizer.state_dict(),
+                    "scheduler": self.scheduler.state_dict()}, os.path.join(path, "net.pth"))
+
+    def load(self, iteration, test=False):
+        path = os.path.join(self.model_path, "net/iteration_{}".format(iteration))
+        saved = torch.load(os.path.join(path, "net.pth"), weights_only=False)
+        self.net.load_state_dict(saved["net"], strict=False)
+        if not test:
+            self.pose.load_state_dict(saved["pose"], strict=False)
+            self.transl.load_state_dict(saved["transl"], strict=False)
+        self.geo_feature.data[...] = saved["geo_feature"].data[...]
+        # optimizer state: only restorable when it was written by this implementation (one flat parameter); a reference
+        # checkpoint's per-tensor Adam moments are dropped
+        if self.optimizer is not None and "optimizer" in saved:
+            try:
+                self.optimizer.load_state_dict(saved["optimizer"])
+            except (ValueError, KeyError):
+                pass
+        if self.scheduler is not None and "scheduler" in saved:
+            self.scheduler.load_state_dict(saved["scheduler"])
+
+    def stage_load(self, ckpt_path):
+        saved = torch.load(os.path.join(ckpt_path, "net.pth"), weights_only=False)
+        self.net.load_state_dict(saved["net"], strict=False)
+        self.pose.load_state_dict(saved["pose"], strict=False)
+        self.transl.load_state_dict(saved["transl"], strict=False)
+        self.geo_feature.data[...] = saved["geo_feature"].data[...]
+
+    def getTrainDataloader(self):
+        return torch.utils.data.DataLoader(self.train_dataset, batch_size=self.batch_size, shuffle=True, num_workers=0, drop_last=True)
+
+    def zero_grad(self, epoch):
+        self.optimizer.zero_grad()
+        if epoch > self.opt_parms.pose_op_start_iter:
+            self.optimizer_pose.zero_grad()
+
+    def step(self, epoch):
+        self.optimizer.step()
+        self.scheduler.step()
+        if epoch > self.opt_parms.pose_op_start_iter:
+            self.optimizer_pose.step()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    def _posed_gaussians(self, idx, iteration, ramp=True):
+        """SMPL -> cano2live -> net (once) -> fused LBS/assembly.  Returns means3D, scales, colors [B,N,3] and dec_out."""
+        pose_batch = self.pose(idx)
+        transl_batch = self.transl(idx)
+        B = pose_batch.shape[0]
+        cano2live = SmplCano2Live.apply(pose_batch, transl_batch, self._rest_joints, self._inv_cano)     # [B,24,12]
+        S = int(self.model_parms.query_posmap_size)
+        dec = self.net.forward_packed(self.geo_feature, S, B)                                             # [S*S, 8]
+        scale_mul = 1e-3 * iteration if (ramp and iteration < 1000) else 1.0                              # avatar_model.py:316-319
+        means, scales, colors = LbsAssemble.apply(dec, cano2live, self.valid_index, self._query_points, self._query_lbs, scale_mul)
+        return means, scales, colors, dec
+
+    def _render_frames(self, batch_data, means, scales, colors):
+        images = []
+        for b in range(means.shape[0]):
+            images.append(render_batch(points=means[b], shs=None, colors_precomp=colors[b], rotations=self.fix_rotation,
+                                       scales=scales[b], opacity=self.fix_opacity, FovX=batch_data["FovX"][b], FovY=batch_data["FovY"][b],
+                                       height=batch_data["height"][b], width=batch_data["width"][b], bg_color=self.background,
+                                       world_view_transform=batch_data["world_view_transform"][b],
+                                       full_proj_transform=batch_data["full_proj_transform"][b], active_sh_degree=0,
+                                       camera_center=batch_data["camera_center"][b]))
+        return torch.stack(images, dim=0)
+
+    def train_stage1(self, batch_data, iteration):
+        """model/avatar_model.py:272-367: returns (images [B,3,H,W], full_pred [B,N,3], offset_loss, geo_loss, scale_loss)."""
+        idx = batch_data["pose_idx"]
+        means, scales, colors, dec = self._posed_gaussians(idx, iteration)
+        # regularisers exactly as the reference forms them (avatar_model.py:328-330): mean over ALL S*S pixels of
+        # (0.02 res)^2 (identical for every frame of the batch), mean of the repeated scales, mean of geo_feature^2
+        offset_loss = torch.mean((dec[:, :3] * 0.02) ** 2)
+        geo_loss = torch.mean(self.geo_feature ** 2)
+        scale_loss = torch.mean(scales)
+        images = self._render_frames(batch_data, means, scales, colors)
+        return images, means, offset_loss, geo_loss, scale_loss
+
+    def train_stage2(self, batch_data, iteration):
+        raise NotImplementedError("train_stage 2 (pose-encoder U-Net) is the next scope row (SURVEY.md §8f rank 2)")
+
+    def render_free_stage1(self, batch_data, iteration):
+        """model/avatar_model.py:467-554: same forward minus the losses (BatchNorm still uses batch statistics)."""
+        if "pose_data" in batch_data:      # novel-pose datasets carry the pose instead of an embedding index
+            pose_batch, transl_batch = batch_data["pose_data"], batch_data["transl_data"]
+            cano2live = SmplCano2Live.apply(pose_batch, transl_batch, self._rest_joints, self._inv_cano)
+            S = int(self.model_parms.query_posmap_size)
+            dec = self.net.forward_packed(self.geo_feature, S, pose_batch.shape[0])
+            scale_mul = 1e-3 * iteration if iteration < 1000 else 1.0
+            means, scales, colors = LbsAssemble.apply(dec, cano2live, self.valid_index, self._query_points, self._query_lbs, scale_mul)
+        else:
+            means, scales, colors, _ = self._posed_gaussians(batch_data["pose_idx"], iteration)
+        return self._render_frames(batch_data, means, scales, colors)
+
+    def render_free_stage2(self, batch_data, iteration):
+        raise NotImplementedError("train_stage 2 (pose-encoder U-Net) is the next scope row (SURVEY.md §8f rank 2)")

@@ -1,0 +1,253 @@
+// Fused Gaussian linear-blend skinning + per-Gaussian attribute assembly, forward + backward.
+//
+// Replaces /root/reference model/avatar_model.py:308-326 (and the identical blocks at :404-424, :499-517, :594-612):
+//   pred_res * 0.02 -> mask-select -> + query_points -> einsum('bnj,bjxy->bnxy') -> einsum('bnxy,bny->bnx') + t,
+//   the iteration<1000 scale ramp, the mask-selects of scales / colours and `repeat(1,1,3)`.
+// The reference materialises pt_mats [B,N,4,4] and runs ~10 kernels + 3 nonzero() host syncs; here one persistent
+// kernel streams the [N,24] skinning-weight table through shared memory with 1-D TMA bulk copies
+// (cp.async.bulk + mbarrier, two stages), reads it ONCE for all B frames of the step, and writes means3D / scales /
+// colours directly in the rasterizer's layout.  Decoder outputs arrive pixel-major packed [S*S, 8] =
+// (res.xyz, scale, rgb, pad); `vidx[n]` is the flat UV index of the n-th valid pixel (order of the boolean mask).
+#include "common.cuh"
+
+namespace ga {
+namespace {
+
+constexpr int kTileN = 256;     // Gaussians per tile == threads per CTA
+constexpr int kJ = 24;
+constexpr int kMaxFrames = 8;
+constexpr int kStages = 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (bytes % 16 == 0, 16-B aligned addresses)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct alignas(128) LbsSmem {
+    float w[kStages][kTileN * kJ];        // 2 x 24 KB skinning-weight tiles (TMA destination)
+    float C[kMaxFrames][kJ * 12];         // cano2live 3x4 per joint, all frames of the step
+    float x[kTileN][13];                  // backward: per-Gaussian [g (x) c | g], padded against bank conflicts
+    uint64_t full[kStages];
+};
+
+template <bool kBackward>
+__global__ void __launch_bounds__(kTileN)
+lbs_kernel(int N, int B, float scale_mul, const float *__restrict__ dec /*[S*S,8]*/, const int32_t *__restrict__ vidx,
+           const float *__restrict__ q /*[N,3]*/, const float *__restrict__ w /*[N,24]*/,
+           const float *__restrict__ Cg /*[B,24,12]*/,
+           // forward outputs
+           float *__restrict__ means, float *__restrict__ scales3, float *__restrict__ colors,
+           // backward inputs / outputs
+           const float *__restrict__ d_means, const float *__restrict__ d_scales3, const float *__restrict__ d_colors,
+           float *__restrict__ d_dec /*[S*S,8], pre-zeroed*/, float *__restrict__ dC /*[B,24,12], pre-zeroed*/)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    LbsSmem &sm = *reinterpret_cast<LbsSmem *>(smem_raw);
+    const int tid = threadIdx.x;
+    const int tiles = (N + kTileN - 1) / kTileN;
+
+    for (int i = tid; i < B * kJ * 12; i += kTileN) sm.C[i / (kJ * 12)][i % (kJ * 12)] = Cg[i];
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int stage) {
+        const int n0 = tile * kTileN;
+        const uint32_t bytes = (uint32_t)min(kTileN, N - n0) * kJ * sizeof(float);
+        mbar_expect_tx(&sm.full[stage], bytes);
+        tma_load_1d(sm.w[stage], w + (size_t)n0 * kJ, bytes, &sm.full[stage]);
+    };
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < tiles) issue(tile, 0);
+
+    float acc[kMaxFrames][2];   // backward: this thread's two dC outputs (o = tid, tid + 256), per frame
+    if (kBackward) {
+#pragma unroll
+        for (int b = 0; b < kMaxFrames; ++b) acc[b][0] = acc[b][1] = 0.f;
+    }
+
+    int it = 0;
+    for (; tile < tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const int next = tile + gridDim.x;
+        if (tid == 0 && next < tiles) issue(next, stage ^ 1);   // the other stage was fully consumed last iteration
+        mbar_wait(&sm.full[stage], (it >> 1) & 1);
+
+        const int n = tile * kTileN + tid;
+        const bool valid = n < N;
+        const float *wr = sm.w[stage] + tid * kJ;
+        float cx = 0.f, cy = 0.f, cz = 0.f, sc = 0.f, r = 0.f, g = 0.f, bl = 0.f;
+        int vi = 0;
+        if (valid) {
+            vi = vidx[n];
+            const float4 o0 = *reinterpret_cast<const float4 *>(dec + (size_t)vi * 8);
+            const float4 o1 = *reinterpret_cast<const float4 *>(dec + (size_t)vi * 8 + 4);
+            cx = q[(size_t)n * 3] + 0.02f * o0.x; cy = q[(size_t)n * 3 + 1] + 0.02f * o0.y; cz = q[(size_t)n * 3 + 2] + 0.02f * o0.z;
+            sc = o0.w * scale_mul; r = o1.x; g = o1.y; bl = o1.z;
+        }
+        float wv[kJ];
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < kJ / 4; ++k) {
+                const float4 t = *reinterpret_cast<const float4 *>(wr + 4 * k);
+                wv[4 * k] = t.x; wv[4 * k + 1] = t.y; wv[4 * k + 2] = t.z; wv[4 * k + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kJ; ++k) wv[k] = 0.f;
+        }
+        float dcx = 0.f, dcy = 0.f, dcz = 0.f, dsc = 0.f, dr = 0.f, dg = 0.f, dbl = 0.f;
+        for (int b = 0; b < B; ++b) {
+            float M[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) M[e] = 0.f;
+#pragma unroll
+            for (int j = 0; j < kJ; ++j) {
+                const float wj = wv[j];
+#pragma unroll
+                for (int e = 0; e < 12; ++e) M[e] = fmaf(wj, sm.C[b][j * 12 + e], M[e]);
+            }
+            const size_t o = ((size_t)b * N + n) * 3;
+            if (!kBackward) {
+                if (valid) {
+                    means[o] = M[0] * cx + M[1] * cy + M[2] * cz + M[3];
+                    means[o + 1] = M[4] * cx + M[5] * cy + M[6] * cz + M[7];
+                    means[o + 2] = M[8] * cx + M[9] * cy + M[10] * cz + M[11];
+                    scales3[o] = sc; scales3[o + 1] = sc; scales3[o + 2] = sc;
+                    colors[o] = r; colors[o + 1] = g; colors[o + 2] = bl;
+                }
+            } else {
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+                if (valid) {
+                    g0 = d_means[o]; g1 = d_means[o + 1]; g2 = d_means[o + 2];
+                    dcx += M[0] * g0 + M[4] * g1 + M[8] * g2;
+                    dcy += M[1] * g0 + M[5] * g1 + M[9] * g2;
+                    dcz += M[2] * g0 + M[6] * g1 + M[10] * g2;
+                    dsc += d_scales3[o] + d_scales3[o + 1] + d_scales3[o + 2];
+                    dr += d_colors[o]; dg += d_colors[o + 1]; dbl += d_colors[o + 2];
+                }
+                // dC[b][j][r*4 + c] += w[n][j] * (c < 3 ? g_r * c_c : g_r): block-level (24 x 256) x (256 x 12) product
+                __syncthreads();
+                float *xr = sm.x[tid];
+                xr[0] = g0 * cx; xr[1] = g0 * cy; xr[2] = g0 * cz; xr[3] = g0;
+                xr[4] = g1 * cx; xr[5] = g1 * cy; xr[6] = g1 * cz; xr[7] = g1;
+                xr[8] = g2 * cx; xr[9] = g2 * cy; xr[10] = g2 * cz; xr[11] = g2;
+                __syncthreads();
+                const float *ws = sm.w[stage];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int oidx = tid + h * kTileN;
+                    if (oidx < kJ * 12) {
+                        const int j = oidx / 12, e = oidx % 12;
+                        float t = 0.f;
+                        const int rows = min(kTileN, N - tile * kTileN);
+                        for (int m = 0; m < rows; ++m) t = fmaf(ws[m * kJ + j], sm.x[m][e], t);
+                        acc[b][h] += t;
+                    }
+                }
+            }
+        }
+        if (kBackward && valid) {
+            float4 o0 = make_float4(0.02f * dcx, 0.02f * dcy, 0.02f * dcz, scale_mul * dsc);
+            float4 o1 = make_float4(dr, dg, dbl, 0.f);
+            *reinterpret_cast<float4 *>(d_dec + (size_t)vi * 8) = o0;
+            *reinterpret_cast<float4 *>(d_dec + (size_t)vi * 8 + 4) = o1;
+        }
+        __syncthreads();   // every thread is done with sm.w[stage] before it is refilled two iterations later
+    }
+    if (kBackward) {
+        for (int b = 0; b < B; ++b)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int oidx = tid + h * kTileN;
+                if (oidx < kJ * 12 && acc[b][h] != 0.f) atomicAdd(&dC[(size_t)b * kJ * 12 + oidx], acc[b][h]);
+            }
+    }
+}
+
+int launch_cfg(int N)
+{
+    const int tiles = cdiv(N, kTileN);
+    return tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs;   // persistent: <= 2 CTAs per SM (2 x ~71 KB smem)
+}
+
+}  // namespace
+}  // namespace ga
+
+using namespace ga;
+
+extern "C" int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, const float *dec_out, const int32_t *valid_index,
+                              const float *query_points, const float *query_lbs, const float *cano2live, float *means3D,
+                              float *scales3, float *colors, void *stream_)
+{
+    GA_REQUIRE(N >= 0 && B >= 1 && B <= kMaxFrames, "bad LBS dims N=%d B=%d (B <= %d)", N, B, kMaxFrames);
+    if (N == 0) return GA_OK;
+    GA_REQUIRE(dec_out && valid_index && query_points && query_lbs && cano2live && means3D && scales3 && colors, "NULL pointer argument");
+    static bool attr_set = false;
+    if (!attr_set) {
+        GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
+        GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
+        attr_set = true;
+    }
+    lbs_kernel<false><<<launch_cfg(N), kTileN, sizeof(LbsSmem), static_cast<cudaStream_t>(stream_)>>>(
+        N, B, scale_mul, dec_out, valid_index, query_points, query_lbs, cano2live, means3D, scales3, colors, nullptr, nullptr,
+        nullptr, nullptr, nullptr);
+    GA_CHECK_LAUNCH("lbs_kernel<fwd>");
+    return GA_OK;
+}
+
+extern "C" int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float scale_mul, const float *dec_out,
+                               const int32_t *valid_index, const float *query_points, const float *query_lbs,
+                               const float *cano2live, const float *d_means3D, const float *d_scales3, const float *d_colors,
+                               float *d_dec_out, float *d_cano2live, void *stream_)
+{
+    GA_REQUIRE(N >= 0 && B >= 1 && B <= kMaxFrames && num_pixels >= N, "bad LBS dims N=%d B=%d pixels=%d", N, B, num_pixels);
+    GA_REQUIRE(d_dec_out && d_cano2live, "NULL pointer argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    GA_CHECK_CUDA(cudaMemsetAsync(d_dec_out, 0, sizeof(float) * 8 * (size_t)num_pixels, stream));
+    GA_CHECK_CUDA(cudaMemsetAsync(d_cano2live, 0, sizeof(float) * kJ * 12 * (size_t)B, stream));
+    if (N == 0) return GA_OK;
+    GA_REQUIRE(dec_out && valid_index && query_points && query_lbs && cano2live && d_means3D && d_scales3 && d_colors, "NULL pointer argument");
+    static bool attr_set = false;
+    if (!attr_set) {
+        GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
+        attr_set = true;
+    }
+    lbs_kernel<true><<<launch_cfg(N), kTileN, sizeof(LbsSmem), stream>>>(N, B, scale_mul, dec_out, valid_index, query_points,
+                                                                        query_lbs, cano2live, nullptr, nullptr, nullptr,
+                                                                        d_means3D, d_scales3, d_colors, d_dec_out, d_cano2live);
+    GA_CHECK_LAUNCH("lbs_kernel<bwd>");
+    return GA_OK;
+}

@@ -95,6 +95,68 @@ typedef struct GaRasterViews {
 int ga_raster_views(const GaRasterSettings *s, const void *geom, const void *binning, const void *img,
                     int64_t num_rendered, GaRasterViews *out);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SMPL joint transforms -> cano2live (model/avatar_model.py:291-296; submodules/smplx/lbs.py:299-405;
+ * body_models.py:380-383).  pose [B,72] axis-angle, transl [B,3], rest_joints [24,3] (J_regressor (v_template +
+ * shapedirs beta), constant per subject), inv_cano [24,4,4] = inv(A_cano) -> cano2live [B,24,12] (3x4 row-major per
+ * joint).  saved_G [B,24,12] is kept by the caller for the backward.
+ * ---------------------------------------------------------------------------------------------------------------- */
+int ga_smpl_forward(int32_t B, const float *pose, const float *transl, const float *rest_joints, const float *inv_cano,
+                    float *cano2live, float *saved_G, void *stream);
+int ga_smpl_backward(int32_t B, const float *pose, const float *rest_joints, const float *inv_cano, const float *saved_G,
+                     const float *d_cano2live, float *d_pose, float *d_transl, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused Gaussian LBS + attribute assembly (model/avatar_model.py:308-326).  dec_out [S*S,8] pixel-major packed decoder
+ * output (res.xyz, scale, rgb, pad); valid_index [N] int32 = flat UV index of the n-th valid pixel; query_points [N,3];
+ * query_lbs [N,24]; cano2live [B,24,12]; scale_mul = 1e-3*iteration if iteration<1000 else 1 (avatar_model.py:316-319).
+ * Outputs per frame in the rasterizer's layout: means3D / scales3 / colors [B,N,3].  B <= 8.
+ * Backward overwrites d_dec_out [num_pixels,8] (zero at invalid pixels) and d_cano2live [B,24,12].
+ * ---------------------------------------------------------------------------------------------------------------- */
+int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, const float *dec_out, const int32_t *valid_index,
+                   const float *query_points, const float *query_lbs, const float *cano2live, float *means3D,
+                   float *scales3, float *colors, void *stream);
+int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float scale_mul, const float *dec_out,
+                    const int32_t *valid_index, const float *query_points, const float *query_lbs, const float *cano2live,
+                    const float *d_means3D, const float *d_scales3, const float *d_colors, float *d_dec_out,
+                    float *d_cano2live, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Stage-1 feature net (model/network.py:39-83; model/modules.py:114-137,508-582,745-754): geometry convs -> bilinear
+ * UV up-sampling -> [features | uv] -> ShapeDecoder with training-mode BatchNorm.  Parameters live in ONE flat fp32
+ * buffer (offsets from ga_decoder_layout, in floats; kernel-friendly packing):
+ *   gconv[i]   [25][64][64]  (tap, c_in, c_out)          <- geom_proc_layers.conv{i+1}.weight [co,ci,5,5]
+ *   w[0]       [128][72]     conv1, input padded 66->72   w[1..3] [128][128] conv2..4
+ *   w[4]       [128][200]    conv5 over [feat(72) | x4(128)]
+ *   w[5]       [384][128]    conv6, conv6N, conv6SH stacked; w[6] [3][128][128] conv7, conv7N, conv7SH
+ *   b/gamma/beta[l]  bias and BatchNorm affine of the same layers (head order xyz, N, SH)
+ *   w8 [8][128]  rows conv8 (3), conv8N (1), conv8SH (3), zero row;  b8 [8]
+ * geo_nchw is `geo_feature` [1,64,feat_res,feat_res]; bn_running [2][1408] running mean / var (nullable);
+ * dec_out [S*S, 8] = (res.xyz, scale, rgb, 0).  The workspace keeps every activation for the backward.
+ * `batch` only enters the unbiased running-variance update: stage-1 inputs are identical across the batch, so the net
+ * is evaluated once per step and d_dec_out must already be summed over the frames.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct GaDecoderDesc {
+    int32_t S, feat_res, batch, c_geom, hsize;
+    float bn_eps, bn_momentum;
+} GaDecoderDesc;
+typedef struct GaDecoderLayout {
+    int64_t gconv[3];
+    int64_t w[7], b[7], gamma[7], beta[7];
+    int64_t w8, b8, total;
+    int32_t bn_channels, bn_offset[7];
+} GaDecoderLayout;
+typedef struct GaDecoderViews {
+    const float *conv3_nhwc, *feat, *y1, *y5, *bn_mean, *bn_rstd, *d_feat;
+} GaDecoderViews;
+int ga_decoder_layout(const GaDecoderDesc *d, GaDecoderLayout *out);
+size_t ga_decoder_workspace_bytes(const GaDecoderDesc *d);
+int ga_decoder_forward(const GaDecoderDesc *d, const float *params, const float *geo_nchw, float *bn_running,
+                       void *workspace, float *dec_out, void *stream);
+int ga_decoder_backward(const GaDecoderDesc *d, const float *params, void *workspace, const float *dec_out,
+                        const float *d_dec_out, float *d_params, float *d_geo_nchw, void *stream);
+int ga_decoder_views(const GaDecoderDesc *d, void *workspace, GaDecoderViews *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,190 @@
+"""GPU parity of the non-rasterizer stages (through the C ABI) against the oracle and against fixtures generated from
+the reference's own modules (tests/golden, oracle/gen_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import avatar_oracle as ao
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+
+# ---------------------------------------------------------------------------------------------------------------- SMPL
+def test_smpl_cano2live_matches_reference_fixture_and_autograd():
+    from gaussianavatar_b200 import synthetic as syn
+    from gaussianavatar_b200.ops import SmplCano2Live
+    d = np.load(os.path.join(GOLD, "smpl_A.npz"))
+    a = syn.make_avatar_assets(100, 16, seed=0)
+    J = torch.tensor(d["rest_joints"])
+    inv_cano = torch.linalg.inv(a.cano_joint_mats)
+    pose = torch.tensor(d["pose"], device=DEV, requires_grad=True)
+    transl = torch.tensor(d["transl"], device=DEV, requires_grad=True)
+    C = SmplCano2Live.apply(pose, transl, J.to(DEV), inv_cano.to(DEV).contiguous())
+    # fixture: A straight from the reference's lbs(); cano2live = A @ inv(A_cano)  (avatar_model.py:296)
+    ref = torch.matmul(torch.tensor(d["A"]), inv_cano[None])[:, :, :3, :].reshape(-1, 24, 12)
+    assert (C.detach().cpu() - ref).abs().max() < 5e-6
+    g = torch.randn(C.shape, generator=torch.Generator().manual_seed(0))
+    (C * g.to(DEV)).sum().backward()
+    p64 = torch.tensor(d["pose"]).double().requires_grad_(True)
+    t64 = torch.tensor(d["transl"]).double().requires_grad_(True)
+    C64 = ao.cano2live(ao.smpl_joint_transforms(J.double(), p64, t64), inv_cano.double()[None])[:, :, :3, :].reshape(-1, 24, 12)
+    (C64 * g.double()).sum().backward()
+    assert _rel(pose.grad.cpu(), p64.grad) < 1e-4
+    assert _rel(transl.grad.cpu(), t64.grad) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------------------------- LBS
+@pytest.mark.parametrize("N,S,B,it", [(1000, 40, 2, 5000), (777, 32, 3, 300), (300, 20, 1, 999)])
+def test_lbs_assemble_forward_backward(N, S, B, it):
+    from gaussianavatar_b200 import synthetic as syn
+    from gaussianavatar_b200.ops import LbsAssemble
+    a = syn.make_avatar_assets(N, S, seed=2)
+    g = torch.Generator().manual_seed(4)
+    dec = torch.randn(S * S, 8, generator=g)
+    dec[:, 3:7] = torch.rand(S * S, 4, generator=g)
+    pose, transl = syn.synthetic_poses(B, seed=1)
+    C = ao.cano2live(ao.smpl_joint_transforms(a.rest_joints, pose, transl), torch.linalg.inv(a.cano_joint_mats)[None])   # [B,24,4,4]
+    vidx = torch.nonzero(a.valid_idx).reshape(-1).to(torch.int32)
+    dec_d = dec.to(DEV).requires_grad_(True)
+    C_d = C[:, :, :3, :].reshape(B, 24, 12).contiguous().to(DEV).requires_grad_(True)
+    mul = 1e-3 * it if it < 1000 else 1.0
+    means, scales, colors = LbsAssemble.apply(dec_d, C_d, vidx.to(DEV), a.query_points.to(DEV), a.query_lbs.to(DEV), mul)
+    dec64 = dec.double().requires_grad_(True)
+    C64 = C.double().requires_grad_(True)
+    o = ao.assemble_and_skin(dec64[:, :3].t()[None].expand(B, -1, -1), dec64[:, 3:4].t()[None].expand(B, -1, -1),
+                             dec64[:, 4:7].t()[None].expand(B, -1, -1), a.valid_idx, a.query_points.double()[None].expand(B, -1, -1),
+                             a.query_lbs.double()[None].expand(B, -1, -1), C64, it)
+    assert (means.detach().cpu() - o["means3D"].detach()).abs().max() < 2e-6
+    assert (scales.detach().cpu() - o["scales"].detach()).abs().max() < 1e-6
+    assert (colors.detach().cpu() - o["colors"].detach()).abs().max() < 1e-6
+    gm, gs, gc = (torch.randn(B, N, 3, generator=g) for _ in range(3))
+    ((means * gm.to(DEV)).sum() + (scales * gs.to(DEV)).sum() + (colors * gc.to(DEV)).sum()).backward()
+    ((o["means3D"] * gm.double()).sum() + (o["scales"] * gs.double()).sum() + (o["colors"] * gc.double()).sum()).backward()
+    assert _rel(dec_d.grad.cpu()[:, :7], dec64.grad[:, :7]) < 1e-5
+    assert _rel(C_d.grad.cpu().reshape(B, 24, 3, 4), C64.grad[:, :, :3, :]) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------------------- decoder
+@pytest.mark.parametrize("name", ["pop_s32_in16.npz", "pop_s32_in32.npz", "pop_s48_in128.npz"])
+def test_decoder_matches_reference_fixture(name):
+    """Forward outputs, BatchNorm running statistics, weight / geo_feature gradients of the reference's POP_no_unet."""
+    from gaussianavatar_b200.network import POP_no_unet
+    d = np.load(os.path.join(GOLD, name))
+    inp, S, B, seed = int(d["inp"]), int(d["S"]), int(d["B"]), int(d["seed"])
+    net = POP_no_unet(c_geom=64, hsize=128).to(DEV)
+    net.load_state_dict(ao.seeded_pop_params(seed), strict=False)
+    g = torch.Generator().manual_seed(seed + 1)
+    geo = (torch.randn(1, 64, inp, inp, generator=g) * 0.01).to(DEV).requires_grad_(True)
+    uv = torch.tensor(d["uv"], device=DEV)
+    res, sc, shs = net(None, geo.expand(B, -1, -1, -1).contiguous(), uv[None].expand(B, -1, -1).contiguous())
+    assert res.shape == (B, 3, S * S) and sc.shape == (B, 1, S * S) and shs.shape == (B, 3, S * S)
+    # strict-FP32 CUDA-core path vs the reference on CPU fp32
+    for got, key, tol in ((res, "res", 2e-4), (sc, "scales", 5e-5), (shs, "shs", 5e-5)):
+        err = np.abs(got.detach().cpu().numpy() - d[key]).max()
+        assert err < tol, (key, err)
+    gr, gs, gc = (torch.randn(res.shape, generator=g), torch.randn(sc.shape, generator=g), torch.randn(shs.shape, generator=g))
+    ((res * gr.to(DEV)).sum() + (sc * gs.to(DEV)).sum() + (shs * gc.to(DEV)).sum()).backward()
+    grads = {k: v.cpu().numpy() for k, v in net.reference_grads().items()}
+    names = [str(n) for n in d["grad_names"]]
+    norms = np.array([np.linalg.norm(grads[n]) for n in names])
+    bias_before_bn = [i for i, n in enumerate(names) if n.endswith(".bias") and "conv8" not in n and ".bn" not in n]
+    keep = [i for i in range(len(names)) if i not in bias_before_bn]
+    assert np.abs(norms[keep] - d["grad_norms"][keep]).max() / d["grad_norms"].max() < 2e-3
+    for k in d.files:
+        if k.startswith("grad:"):
+            n = k[5:]
+            if n in ("decoder.conv1.bias", "decoder.conv6N.bias"):
+                assert np.abs(grads[n]).max() < 5e-3      # exactly-zero gradient (bias in front of BatchNorm)
+                continue
+            got = grads[n][:8, :8] if n.startswith("geom_proc") else grads[n]
+            assert _rel(got, d[k]) < 3e-3, (n, _rel(got, d[k]))
+    gg = geo.grad.cpu().numpy()
+    assert abs(np.linalg.norm(gg) - float(d["geo_grad_norm"])) / float(d["geo_grad_norm"]) < 2e-3
+    assert _rel(gg[:, ::4, ::max(1, inp // 8), ::max(1, inp // 8)], d["geo_grad_sub"]) < 3e-3
+    sd = net.state_dict()
+    assert np.abs(sd["decoder.bn1.running_mean"].cpu().numpy() - d["bn1_running_mean"]).max() < 1e-5
+    assert np.abs(sd["decoder.bn1.running_var"].cpu().numpy() - d["bn1_running_var"]).max() < 1e-5
+
+
+def test_decoder_state_dict_roundtrip_reference_names():
+    from gaussianavatar_b200.network import POP_no_unet
+    net = POP_no_unet(c_geom=64, hsize=128).to(DEV)
+    p = ao.seeded_pop_params(11)
+    net.load_state_dict(p, strict=False)
+    sd = net.state_dict()
+    for k, v in p.items():
+        assert torch.equal(sd[k].cpu(), v), k
+    assert "decoder.bn7SH.running_var" in sd and "decoder.bn1.num_batches_tracked" in sd
+    assert sum(v.numel() for k, v in sd.items() if "running" not in k and "num_batches" not in k) == 493063
+
+
+# -------------------------------------------------------------------------------------------------------- end to end
+def _make_model(N, S, side, B, seed=0, inp=32):
+    from gaussianavatar_b200 import synthetic as syn
+    from gaussianavatar_b200.avatar_model import AvatarModel
+    from gaussianavatar_b200.camera import TEST_POSE_EXTRINSIC, TEST_POSE_K, make_camera, scaled_intrinsics
+    assets = syn.make_avatar_assets(N, S, seed=seed)
+    tp = np.load(os.path.join(GOLD, "test_pose_subset.npz"))
+    pose, transl = torch.tensor(tp["body_pose"]), torch.tensor(tp["trans"])
+    cam = make_camera(scaled_intrinsics(TEST_POSE_K, side), TEST_POSE_EXTRINSIC, side, side)
+    frames = [dict(pose_idx=i, FovX=cam.FovX, FovY=cam.FovY, height=side, width=side, world_view_transform=cam.world_view_transform,
+                   full_proj_transform=cam.full_proj_transform, camera_center=cam.camera_center) for i in range(pose.shape[0])]
+    torch.manual_seed(seed)
+    model = AvatarModel.from_assets(assets, frames, pose, transl, batch_size=B, device=DEV)
+    model.model_parms.inp_posmap_size = inp
+    model.net_set(1)
+    return model, assets, cam, pose, transl
+
+
+def test_train_stage1_end_to_end_vs_oracle_chain():
+    """Whole frame: SMPL -> net -> LBS -> rasterizer vs the chain of oracles (image mean-L1 <= 1e-4)."""
+    from oracle import raster_oracle as ro
+    import math
+    N, S, side, B = 3000, 64, 128, 2
+    model, assets, cam, pose, transl = _make_model(N, S, side, B)
+    with torch.no_grad():
+        # make the Gaussians visible: scale head bias -> sigmoid ~ 0.02 m
+        sd = model.net.state_dict()
+        sd["decoder.conv8N.bias"] = torch.tensor([-3.9])
+        model.net.load_state_dict(sd, strict=False)
+    idx = torch.tensor([3, 17], device=DEV)
+    batch = dict(pose_idx=idx, FovX=[cam.FovX] * B, FovY=[cam.FovY] * B, height=[side] * B, width=[side] * B,
+                 world_view_transform=[cam.world_view_transform.to(DEV)] * B, full_proj_transform=[cam.full_proj_transform.to(DEV)] * B,
+                 camera_center=[cam.camera_center.to(DEV)] * B)
+    images, full_pred, offset_loss, geo_loss, scale_loss = model.train_stage1(batch, 5000)
+    assert images.shape == (B, 3, side, side) and full_pred.shape == (B, N, 3)
+    # oracle chain on CPU
+    p = {k: v.cpu() for k, v in model.net.state_dict().items() if "running" not in k and "num_batches" not in k}
+    geo = model.geo_feature.detach().cpu()
+    res, sc, shs = ao.pop_forward(p, geo, S, B=B)
+    A = ao.smpl_joint_transforms(assets.rest_joints, pose[idx.cpu()], transl[idx.cpu()])
+    C = ao.cano2live(A, torch.linalg.inv(assets.cano_joint_mats)[None])
+    o = ao.assemble_and_skin(res, sc, shs, assets.valid_idx, assets.query_points[None].expand(B, -1, -1),
+                             assets.query_lbs[None].expand(B, -1, -1), C, 5000, geo_feature=geo)
+    assert (full_pred.detach().cpu() - o["means3D"]).abs().max() < 5e-5
+    assert abs(offset_loss.item() - o["offset_loss"].item()) < 1e-6 * max(1, abs(o["offset_loss"].item()))
+    assert abs(scale_loss.item() - o["scale_loss"].item()) < 1e-6
+    assert abs(geo_loss.item() - o["geo_loss"].item()) < 1e-9
+    rots = np.zeros((N, 4), np.float32); rots[:, 0] = 1
+    for b in range(B):
+        ref = ro.forward(o["means3D"][b].numpy(), o["colors"][b].numpy(), np.ones(N, np.float32), o["scales"][b].numpy(), rots,
+                         np.ones(3, np.float32), cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(),
+                         math.tan(cam.FovX / 2), math.tan(cam.FovY / 2), side, side)
+        err = np.abs(images[b].detach().cpu().numpy() - ref.image).mean()
+        assert err <= 1e-4, err
+        assert (ref.image < 0.99).mean() > 0.02      # the body is actually on screen
+    # and the whole thing back-propagates into every trainable tensor
+    loss = images.mean() + offset_loss + geo_loss + scale_loss
+    loss.backward()
+    assert model.net.flat.grad is not None and torch.isfinite(model.net.flat.grad).all() and model.net.flat.grad.abs().sum() > 0
+    assert model.geo_feature.grad is not None and torch.isfinite(model.geo_feature.grad).all()
+    assert model.pose.weight.grad is not None
