@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Headline benchmark: stage-1 train-step FPS at 200k Gaussians / 1024^2 (BASELINE.json configs[2]; configs[3] semantics
+for N > 1: every rank renders its own frames, one all-reduce of the shared feature-net gradients).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU arm: the reference's algorithm (oracle port) on the host cores
+
+One "step" = SMPL pose -> feature net -> LBS -> rasterize B frames -> L1+SSIM loss -> backward -> Adam (train.py:66-97).
+Rank 0 prints ONE JSON line.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over
+ranks.  `value` has inputs resident in HBM; `e2e` goes through the public API with HOST (pinned) batches, the H2D copy
+and the loss read-back inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train_step_fps_200k_gaussians_1024sq"
+UNIT = "frames/s"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self._p = gpu_index, [], None
+
+    def start(self):
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                        "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self._p = None
+
+    def _read(self):
+        for line in self._p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self._p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self._p.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        d["_source"] = "measured (MEASURED_PEAKS.json)"
+        return d
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback (B200_PROFILING.md)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm for the same step, restated in oracle/ (the reference itself cannot travel to the GPU
+# box: it needs /root/reference plus CUDA-only / un-installed dependencies).  One step = ONE frame at full size.
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(config: int):
+    import math
+    import numpy as np
+    import torch
+    from gaussianavatar_b200 import synthetic as syn
+    from gaussianavatar_b200.camera import TEST_POSE_EXTRINSIC, TEST_POSE_K, make_camera, scaled_intrinsics
+    from gaussianavatar_b200.workload import load_poses
+    from oracle import avatar_oracle as ao
+    from oracle import raster_oracle as ro
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    N, S, side = syn.CONFIGS[config]
+    a = syn.make_avatar_assets(N, S, seed=0)
+    pose, transl, _ = load_poses(32)
+    cam = make_camera(scaled_intrinsics(TEST_POSE_K, side), TEST_POSE_EXTRINSIC, side, side)
+    p = {k: v.clone().requires_grad_(True) for k, v in ao.seeded_pop_params(0).items()}
+    with torch.no_grad():
+        p["decoder.conv8N.bias"].fill_(-5.3)
+        for k in p:
+            if ".bn" in k:
+                p[k].copy_(torch.ones_like(p[k]) if k.endswith("weight") else torch.zeros_like(p[k]))
+    geo = (torch.randn(1, 64, 128, 128, generator=torch.Generator().manual_seed(0)) * 0.01).requires_grad_(True)
+    opt = torch.optim.Adam([{"params": list(p.values()), "lr": 3e-3}, {"params": [geo], "lr": 5e-4}])
+    inv_cano = torch.linalg.inv(a.cano_joint_mats)[None]
+    rots = np.zeros((N, 4), np.float32); rots[:, 0] = 1
+    gt = torch.rand(1, 3, side, side, generator=torch.Generator().manual_seed(2))
+    tanx, tany = math.tan(cam.FovX / 2), math.tan(cam.FovY / 2)
+
+    def step(i: int):
+        f = i % pose.shape[0]
+        ps = pose[f:f + 1].clone().requires_grad_(True)
+        tr = transl[f:f + 1].clone().requires_grad_(True)
+        res, sc, shs = ao.pop_forward(p, geo, S, B=1)
+        C = ao.cano2live(ao.smpl_joint_transforms(a.rest_joints, ps, tr), inv_cano)
+        o = ao.assemble_and_skin(res, sc, shs, a.valid_idx, a.query_points[None], a.query_lbs[None], C, 5000, geo_feature=geo)
+        means, colors, scales = o["means3D"][0], o["colors"][0], o["scales"][0]
+        r = ro.forward(means.detach().numpy(), colors.detach().numpy(), np.ones(N, np.float32), scales.detach().numpy(), rots,
+                       np.ones(3, np.float32), cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(), tanx, tany, side, side)
+        img = torch.tensor(r.image, dtype=torch.float32)[None].requires_grad_(True)
+        loss_img = 0.8 * ao.l1_loss_w(img, gt) + 0.2 * (1.0 - ao.ssim(img, gt))
+        loss_img.backward()
+        gb = r.backward(img.grad[0].numpy())
+        opt.zero_grad()
+        reg = 3e-2 * o["scale_loss"] + 10.0 * o["offset_loss"] + o["geo_loss"]
+        torch.autograd.backward([means, colors, scales, reg],
+                                [torch.tensor(gb["d_means3D"], dtype=torch.float32), torch.tensor(gb["d_colors"], dtype=torch.float32),
+                                 torch.tensor(gb["d_scales"], dtype=torch.float32), torch.ones(())])
+        opt.step()
+        r.close()
+        return float(loss_img.detach())
+
+    return step, dict(N=N, S=S, side=side)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    step, dims = cpu_reference_step_factory(args.config)
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter(); step(0); t_first = time.perf_counter() - t0      # first call also warms the allocator
+    budget_s = 200.0
+    warm = max(0, min(args.warmup, int(0.25 * budget_s / max(t_first, 1e-3)) - 1))
+    for i in range(warm):
+        step(1 + i)
+    steps = max(1, min(args.steps, int(0.75 * budget_s / max(t_first, 1e-3))))
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(1 + warm + i)
+    dt = time.perf_counter() - t0
+    fps = steps / dt
+    sample = (f"{steps} of the requested {args.steps} steps executed (bounded to ~{budget_s:.0f}s of CPU work); one step = ONE "
+              f"{dims['N']}-Gaussian / {dims['side']}^2 frame: feature net + SMPL + LBS (torch CPU, {torch.get_num_threads()} threads) + C/OpenMP "
+              f"rasterizer fwd+bwd + L1/SSIM + Adam")
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"config{args.config}: {dims['N']} Gaussians, {dims['side']}x{dims['side']}, stage-1 train step, 1 frame/step on host cores"},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def algorithmic_cost(N, S, side, R, B):
+    """Per-launch algorithmic bytes / flops of the kernels we report rooflines for."""
+    M = S * S
+    T = ((side + 15) // 16) ** 2
+    bits = 32 + max(1, (T - 1).bit_length())
+    passes = (bits + 7) // 8
+    raster_fwd_bytes = N * (56 + 40 + 8) + R * (12 + 8 + passes * 24 + 8 + 40) + side * side * 20 + T * 8
+    return dict(
+        raster_fwd_bytes=raster_fwd_bytes,
+        mlp_layer_fwd_flops=2.0 * M * 128 * 128, mlp_layer_fwd_bytes=2.0 * M * 128 * 4,
+        mlp_fwd_flops=363264.0 * M, mlp_fwdbwd_flops=3 * 363264.0 * M,
+        lbs_bytes=N * (96 + 12 + 32 + 4) + B * N * 36)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3, help="BASELINE.md §4 config number (3 = 200k / 1024^2 stage-1 loop)")
+    ap.add_argument("--frames-per-gpu", type=int, default=2, help="frames per step and GPU (reference batch_size=2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from gaussianavatar_b200 import _lib
+    from gaussianavatar_b200.trainer import Stage1Trainer
+    from gaussianavatar_b200.workload import Stage1Workload, to_cuda
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.frames_per_gpu
+
+    wl = Stage1Workload(args.config, B, device=dev)
+    wl.make_ground_truth()
+    trainer = Stage1Trainer(wl.model, fused_adam=True)
+    iteration0 = 5000      # >= 1000: no scale ramp
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def run_value(n, start):
+        for i in range(n):
+            batch = wl.device_batch(wl.frame_ids(start + i, rank, world))
+            trainer.step(batch, iteration0 + start + i, epoch=1)
+
+    h2d_bytes = [0]
+
+    def run_e2e(n, start):
+        last = 0.0
+        for i in range(n):
+            hb = wl.host_batch(wl.frame_ids(start + i, rank, world))
+            batch, nb = to_cuda(hb, dev)
+            h2d_bytes[0] = nb
+            loss = trainer.step(batch, iteration0 + start + i, epoch=1)
+            last = loss.item()                 # device -> host read of the step's result (train.py:101)
+        return last
+
+    def timed(fn, n, start):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(n, start)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- warm-up, then the timed region (inputs resident in HBM) -------------------------------------------------------
+    run_value(args.warmup, 0)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    ms_value = timed(run_value, args.steps, args.warmup)
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else {}
+    fps = world * B * args.steps / (ms_value * 1e-3)
+
+    # ---- end to end through the public API with host batches ----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        run_e2e(2, args.warmup + args.steps)
+        ms_e2e = timed(run_e2e, args.steps, args.warmup + args.steps + 2)
+        e2e = {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes[0]),
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps}
+
+    # ---- per-kernel CUDA-event pass (same steps again, rank-local) -> roofline ---------------------------------------
+    _lib.profile(True)
+    _lib.profile_report()
+    nprof = min(args.steps, 5)
+    run_value(nprof, 2 * args.warmup + 2 * args.steps + 4)
+    prof = _lib.profile_report()
+    _lib.profile(False)
+    per_step = {k: (n / nprof, ms / nprof) for k, (n, ms) in prof.items()}
+    total_kernel_ms = sum(ms for _, ms in per_step.values())
+
+    peaks = measured_peaks()
+    # the rasterizer's instance count for the cost model (one forward outside the timed region)
+    with torch.no_grad():
+        from gaussianavatar_b200.rasterizer import GaussianRasterizationSettings, rasterize_forward
+        import math
+        bt = wl.device_batch(wl.frame_ids(0, rank, world))
+        means, scales, colors, _ = wl.model._posed_gaussians(bt["pose_idx"], iteration0)
+        c = wl._cam_dev
+        rs = GaussianRasterizationSettings(c.height, c.width, math.tan(c.FovX / 2), math.tan(c.FovY / 2), wl.model.background, 1.0,
+                                           c.world_view_transform, c.full_proj_transform, 0, c.camera_center, False, False)
+        _, _, rctx = rasterize_forward(means[0], colors[0], wl.model.fix_opacity, scales[0], wl.model.fix_rotation, rs)
+        R = rctx.num_rendered
+    cost = algorithmic_cost(wl.N, wl.S, wl.side, R, B)
+
+    def kms(*names):
+        return sum(per_step[n][1] for n in names if n in per_step)
+
+    mlp_names = [n for n in per_step if n.startswith("mlp_")]
+    mlp_ms = kms(*mlp_names)
+    raster_fwd_names = ["preprocess_fwd_kernel", "cub_inclusive_sum", "duplicate_with_keys_kernel", "cub_radix_sort_pairs",
+                        "tile_ranges_kernel", "render_fwd_kernel"]
+    raster_fwd_ms = kms(*raster_fwd_names) / B          # per frame
+    raster_bwd_ms = kms("render_bwd_kernel", "preprocess_bwd_kernel") / B
+    dominant = max(per_step.items(), key=lambda kv: kv[1][1])[0] if per_step else None
+    # dominant kernel family: the decoder-MLP GEMMs (strict-FP32 CUDA-core path in this round)
+    mlp_tflops = cost["mlp_fwdbwd_flops"] / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else None
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    roofline = {"kernel": "decoder MLP GEMMs (mlp_fwd_* + mlp_dgrad_* + mlp_wgrad_*), all launches of one step",
+                "bound": "tensor", "achieved": mlp_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": (mlp_tflops / tf32_peak) if mlp_tflops else None, "traffic": None,
+                "peak_source": peaks["_source"] + "; tf32 dense = 1/2 x bf16 sustained", "ms_per_step": mlp_ms,
+                "share_of_kernel_time": mlp_ms / total_kernel_ms if total_kernel_ms else None}
+    raster_gbs = cost["raster_fwd_bytes"] / (raster_fwd_ms * 1e-3) / 1e9 if raster_fwd_ms > 0 else None
+    raster_roofline = {"kernel": "rasterizer forward K1-K6, per frame", "bound": "hbm", "achieved": raster_gbs, "peak": peaks["hbm_gbs"],
+                       "unit": "GB/s", "frac": raster_gbs / peaks["hbm_gbs"] if raster_gbs else None, "traffic": None,
+                       "algorithmic_bytes": cost["raster_fwd_bytes"], "ms_per_frame": raster_fwd_ms, "num_rendered": R,
+                       "bwd_ms_per_frame": raster_bwd_ms, "peak_source": peaks["_source"]}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        torch.cuda.synchronize()
+        step, dims = cpu_reference_step_factory(args.config)
+        step(0)
+        t0 = time.perf_counter(); n = 0
+        while n < 2 or (time.perf_counter() - t0 < 12.0 and n < 8):
+            step(1 + n); n += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"{n} full-size single-frame train steps of the oracle port (torch CPU all cores + C/OpenMP rasterizer), {dt:.1f}s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"config{args.config}: {wl.N} Gaussians, UV {wl.S}^2, {wl.side}x{wl.side}, stage-1 train step (feature net + "
+                                       f"L1/SSIM), {B} frames/GPU/step, global batch {B * world}", "poses": wl.pose_source,
+                           "l2_policy": "inputs and activations (>1.5 GB/step) exceed the 126 MB L2; no explicit flush",
+                           "parallelism": f"dp{world} (frames sharded, 1 all-reduce of 1.56M fp32 grads)"},
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "raster_roofline": raster_roofline,
+                "cpu_baseline": cpu_baseline,
+                "kernel_ms_per_step": {k: round(v[1], 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1][1])},
+                "dominant_kernel": dominant}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier(device_ids=[local])
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

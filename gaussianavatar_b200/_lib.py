@@ -45,6 +45,8 @@ _SIGNATURES = {
     "ga_version": (ctypes.c_int, []),
     "ga_last_error": (ctypes.c_char_p, []),
     "ga_launch_count": (ctypes.c_longlong, []),
+    "ga_profile_enable": (None, [ctypes.c_int]),
+    "ga_profile_report": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t]),
     "ga_raster_geom_bytes": (ctypes.c_size_t, [ctypes.c_int32]),
     "ga_raster_img_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
     "ga_raster_binning_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
@@ -61,6 +63,10 @@ _SIGNATURES = {
     "ga_decoder_forward": (ctypes.c_int, [ctypes.POINTER(GaDecoderDesc)] + [c_vp] * 6),
     "ga_decoder_backward": (ctypes.c_int, [ctypes.POINTER(GaDecoderDesc)] + [c_vp] * 7),
     "ga_decoder_views": (ctypes.c_int, [ctypes.POINTER(GaDecoderDesc), c_vp, ctypes.POINTER(GaDecoderViews)]),
+    "ga_loss_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 3),
+    "ga_loss_forward": (ctypes.c_int, [ctypes.c_int32] * 3 + [c_vp, c_vp, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp]),
+    "ga_loss_backward": (ctypes.c_int, [ctypes.c_int32] * 3 + [c_vp, c_vp, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),
+    "ga_adam_step": (ctypes.c_int, [ctypes.c_int64, c_vp, c_vp, c_vp, c_vp] + [ctypes.c_float] * 4 + [ctypes.c_int64, ctypes.c_float, c_vp]),
     "ga_raster_views": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings), c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(GaRasterViews)]),
 }
 
@@ -95,6 +101,21 @@ def ptr(t) -> int | None:
     if t is None:
         return None
     return t.data_ptr()
+
+
+def profile(on: bool) -> None:
+    lib().ga_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """{kernel name: (launches, total_ms)} since the last report; synchronises the device."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().ga_profile_report(buf, len(buf)), "ga_profile_report")
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(" ", 2)
+        out[name] = (int(n), float(ms))
+    return out
 
 
 def launch_count() -> int:

@@ -11,6 +11,14 @@ namespace ga {
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);
+// Optional per-kernel CUDA-event timing (bench.py's roofline leg): begin/end bracket one launch on its stream.
+void prof_begin(cudaStream_t st);
+void prof_end(const char *name, cudaStream_t st);
+struct ProfScope {
+    const char *name; cudaStream_t st;
+    ProfScope(const char *n, cudaStream_t s) : name(n), st(s) { prof_begin(s); }
+    ~ProfScope() { prof_end(name, st); }
+};
 
 #define GA_CHECK_CUDA(expr)                                                                          \
     do {                                                                                             \

@@ -441,7 +441,10 @@ int launch_gemm(const char *name, const AL &A, const BL &B, const EP &E, int Mg,
         splits = cdiv(Kg, kps);
     } else splits = 1;
     dim3 grid(cdiv(Mg, BM), cdiv(Ng, BN), splits);
-    gemm_kernel<BM, BN, AL, BL, EP><<<grid, kGemmThreads, 0, st>>>(A, B, E, Kg, kps);
+    {
+        ProfScope _ps(name, st);
+        gemm_kernel<BM, BN, AL, BL, EP><<<grid, kGemmThreads, 0, st>>>(A, B, E, Kg, kps);
+    }
     GA_CHECK_LAUNCH(name);
     return GA_OK;
 }
@@ -499,7 +502,10 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
     const int S = d->S, Hf = d->feat_res, P = Hf * Hf;
     const int M = S * S;
 
-    chw_to_hwc_kernel<<<cdiv(P, 64), 256, 0, st>>>(geo_nchw, w.F[0], P);
+    {
+        ProfScope _ps("chw_to_hwc_kernel", st);
+        chw_to_hwc_kernel<<<cdiv(P, 64), 256, 0, st>>>(geo_nchw, w.F[0], P);
+    }
     GA_CHECK_LAUNCH("chw_to_hwc_kernel");
     for (int i = 0; i < 3; ++i) {
         ALoadIm2colK<128> A{w.F[i], Hf, +1, P};
@@ -507,16 +513,22 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
         EpiStoreStats E{w.F[i + 1], kCg, P, kCg, nullptr, nullptr, nullptr, false};
         if (int rc = launch_gemm<128, 64>("geom_conv_fwd", A, B, E, P, kCg, 25 * kCg, 1, st)) return rc;
     }
-    sample_feat_fwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, w.F[3], w.feat);
+    {
+        ProfScope _ps("sample_feat_fwd_kernel", st);
+        sample_feat_fwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, w.F[3], w.feat);
+    }
     GA_CHECK_LAUNCH("sample_feat_fwd_kernel");
     GA_CHECK_CUDA(cudaMemsetAsync(w.stat, 0, sizeof(double) * 2 * kBnCh, st));
 
     double *sum = w.stat, *sumsq = w.stat + kBnCh;
     auto finalize = [&](int l, int C) -> int {
         const int o = kBnOff[l];
-        bn_finalize_fwd_kernel<<<cdiv(C, 128), 128, 0, st>>>(C, (double)M, (double)M * d->batch, d->bn_eps, d->bn_momentum, sum + o, sumsq + o,
-                                                             params + L.gamma[l] , params + L.beta[l], cf.mean + o, cf.rstd + o, cf.a + o, cf.b + o,
-                                                             bn_running ? bn_running + o : nullptr, bn_running ? bn_running + kBnCh + o : nullptr);
+        {
+            ProfScope _ps("bn_finalize_fwd_kernel", st);
+            bn_finalize_fwd_kernel<<<cdiv(C, 128), 128, 0, st>>>(C, (double)M, (double)M * d->batch, d->bn_eps, d->bn_momentum, sum + o, sumsq + o,
+                                                                 params + L.gamma[l] , params + L.beta[l], cf.mean + o, cf.rstd + o, cf.a + o, cf.b + o,
+                                                                 bn_running ? bn_running + o : nullptr, bn_running ? bn_running + kBnCh + o : nullptr);
+        }
         GA_CHECK_LAUNCH("bn_finalize_fwd_kernel");
         return GA_OK;
     };
@@ -556,7 +568,10 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
         if (int rc = launch_gemm<128, 128>("mlp_fwd_l7", A, B, E, M, kH, kH, 1, st)) return rc;
     }
     if (int rc = finalize(6, 3 * kH)) return rc;
-    heads_fwd_kernel<<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
+    {
+        ProfScope _ps("heads_fwd_kernel", st);
+        heads_fwd_kernel<<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
+    }
     GA_CHECK_LAUNCH("heads_fwd_kernel");
     return GA_OK;
 }
@@ -580,8 +595,11 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
 
     auto finalize = [&](int l, int C) -> int {
         const int o = kBnOff[l];
-        bn_finalize_bwd_kernel<<<cdiv(C, 128), 128, 0, st>>>(C, (double)M, s1 + o, s2 + o, params + L.gamma[l], cf.rstd + o, cf.ga + o, cf.m1 + o,
-                                                             cf.m2 + o, d_params + L.gamma[l], d_params + L.beta[l]);
+        {
+            ProfScope _ps("bn_finalize_bwd_kernel", st);
+            bn_finalize_bwd_kernel<<<cdiv(C, 128), 128, 0, st>>>(C, (double)M, s1 + o, s2 + o, params + L.gamma[l], cf.rstd + o, cf.ga + o, cf.m1 + o,
+                                                                 cf.m2 + o, d_params + L.gamma[l], d_params + L.beta[l]);
+        }
         GA_CHECK_LAUNCH("bn_finalize_bwd_kernel");
         return GA_OK;
     };
@@ -590,14 +608,23 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
     // heads: d_dec_out -> dZ7 (+ dW8, db8)
     {
         const int o7 = kBnOff[6];
-        heads_bwd_kernel<0><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8, dec_out,
-                                                         d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+        {
+            ProfScope _ps("heads_bwd_kernel<0>", st);
+            heads_bwd_kernel<0><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8, dec_out,
+                                                             d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+        }
         GA_CHECK_LAUNCH("heads_bwd_kernel<0>");
-        heads_bwd_kernel<1><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8, dec_out,
-                                                         d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+        {
+            ProfScope _ps("heads_bwd_kernel<1>", st);
+            heads_bwd_kernel<1><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8, dec_out,
+                                                             d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+        }
         GA_CHECK_LAUNCH("heads_bwd_kernel<1>");
-        heads_bwd_kernel<2><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8, dec_out,
-                                                         d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+        {
+            ProfScope _ps("heads_bwd_kernel<2>", st);
+            heads_bwd_kernel<2><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8, dec_out,
+                                                             d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+        }
         GA_CHECK_LAUNCH("heads_bwd_kernel<2>");
         if (int rc = finalize(6, 3 * kH)) return rc;
     }
@@ -673,7 +700,10 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
     }
     // up-sampling backward, then the three convs
     GA_CHECK_CUDA(cudaMemsetAsync(w.dF[0], 0, sizeof(float) * (size_t)P * kCg, st));
-    sample_feat_bwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, w.d_feat, w.dF[0]);
+    {
+        ProfScope _ps("sample_feat_bwd_kernel", st);
+        sample_feat_bwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, w.d_feat, w.dF[0]);
+    }
     GA_CHECK_LAUNCH("sample_feat_bwd_kernel");
     float *dcur = w.dF[0], *dnxt = w.dF[1];
     for (int i = 2; i >= 0; --i) {
@@ -691,7 +721,10 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         }
         float *t = dcur; dcur = dnxt; dnxt = t;
     }
-    hwc_to_chw_kernel<<<cdiv(P, 64), 256, 0, st>>>(dcur, d_geo_nchw, P);
+    {
+        ProfScope _ps("hwc_to_chw_kernel", st);
+        hwc_to_chw_kernel<<<cdiv(P, 64), 256, 0, st>>>(dcur, d_geo_nchw, P);
+    }
     GA_CHECK_LAUNCH("hwc_to_chw_kernel");
     return GA_OK;
 }

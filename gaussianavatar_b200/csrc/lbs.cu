@@ -221,9 +221,9 @@ extern "C" int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, const float
         GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
         attr_set = true;
     }
-    lbs_kernel<false><<<launch_cfg(N), kTileN, sizeof(LbsSmem), static_cast<cudaStream_t>(stream_)>>>(
+    { ProfScope _ps("lbs_kernel<fwd>", static_cast<cudaStream_t>(stream_)); lbs_kernel<false><<<launch_cfg(N), kTileN, sizeof(LbsSmem), static_cast<cudaStream_t>(stream_)>>>(
         N, B, scale_mul, dec_out, valid_index, query_points, query_lbs, cano2live, means3D, scales3, colors, nullptr, nullptr,
-        nullptr, nullptr, nullptr);
+        nullptr, nullptr, nullptr); }
     GA_CHECK_LAUNCH("lbs_kernel<fwd>");
     return GA_OK;
 }
@@ -245,9 +245,9 @@ extern "C" int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float s
         GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
         attr_set = true;
     }
-    lbs_kernel<true><<<launch_cfg(N), kTileN, sizeof(LbsSmem), stream>>>(N, B, scale_mul, dec_out, valid_index, query_points,
+    { ProfScope _ps("lbs_kernel<bwd>", stream); lbs_kernel<true><<<launch_cfg(N), kTileN, sizeof(LbsSmem), stream>>>(N, B, scale_mul, dec_out, valid_index, query_points,
                                                                         query_lbs, cano2live, nullptr, nullptr, nullptr,
-                                                                        d_means3D, d_scales3, d_colors, d_dec_out, d_cano2live);
+                                                                        d_means3D, d_scales3, d_colors, d_dec_out, d_cano2live); }
     GA_CHECK_LAUNCH("lbs_kernel<bwd>");
     return GA_OK;
 }

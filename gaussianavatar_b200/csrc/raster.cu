@@ -653,13 +653,19 @@ extern "C" int ga_raster_forward_preprocess(const GaRasterSettings *s, const flo
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     GeomViews g = carve_geom(geom, s->P);
     const int gx = cdiv(s->W, kTile), gy = cdiv(s->H, kTile);
-    preprocess_fwd_kernel<<<cdiv(s->P, 256), 256, 0, stream>>>(s->P, s->H, s->W, gx, gy, s->tanfovx, s->tanfovy,
-                                                              s->scale_modifier, means3D, scales, rotations, opacities,
-                                                              viewmatrix, projmatrix, g.depth, g.xy, g.conic_o, g.cov3d,
-                                                              g.tiles, g.rect, radii);
+    {
+        ProfScope _ps("preprocess_fwd_kernel", stream);
+        preprocess_fwd_kernel<<<cdiv(s->P, 256), 256, 0, stream>>>(s->P, s->H, s->W, gx, gy, s->tanfovx, s->tanfovy,
+                                                                  s->scale_modifier, means3D, scales, rotations, opacities,
+                                                                  viewmatrix, projmatrix, g.depth, g.xy, g.conic_o, g.cov3d,
+                                                                  g.tiles, g.rect, radii);
+    }
     GA_CHECK_LAUNCH("preprocess_fwd_kernel");
     size_t tb = g.scan_temp_bytes;
-    GA_CHECK_CUDA(cub::DeviceScan::InclusiveSum(g.scan_temp, tb, g.tiles, g.offsets, s->P, stream));
+    {
+        ProfScope _ps("cub_inclusive_sum", stream);
+        GA_CHECK_CUDA(cub::DeviceScan::InclusiveSum(g.scan_temp, tb, g.tiles, g.offsets, s->P, stream));
+    }
     uint32_t total = 0;
     GA_CHECK_CUDA(cudaMemcpyAsync(&total, g.offsets + (s->P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     GA_CHECK_CUDA(cudaStreamSynchronize(stream));
@@ -687,18 +693,30 @@ extern "C" int ga_raster_forward_render(const GaRasterSettings *s, const float *
             return GA_ERR_CAPACITY;
         }
         GeomViews g = carve_geom(geom, s->P);
-        duplicate_with_keys_kernel<<<cdiv(s->P, 256), 256, 0, stream>>>(s->P, gx, g.depth, g.offsets, g.tiles, g.rect,
-                                                                       b.keys_unsorted, b.vals_unsorted);
+        {
+            ProfScope _ps("duplicate_with_keys_kernel", stream);
+            duplicate_with_keys_kernel<<<cdiv(s->P, 256), 256, 0, stream>>>(s->P, gx, g.depth, g.offsets, g.tiles, g.rect,
+                                                                           b.keys_unsorted, b.vals_unsorted);
+        }
         GA_CHECK_LAUNCH("duplicate_with_keys_kernel");
         size_t tb = b.sort_temp_bytes;
-        GA_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.sort_temp, tb, b.keys_unsorted, b.keys, b.vals_unsorted, b.vals,
-                                                      (int)R, 0, sort_end_bit(s->H, s->W), stream));
-        tile_ranges_kernel<<<cdiv(R, 256), 256, 0, stream>>>(R, b.keys, iv.ranges);
+        {
+            ProfScope _ps("cub_radix_sort_pairs", stream);
+            GA_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.sort_temp, tb, b.keys_unsorted, b.keys, b.vals_unsorted, b.vals,
+                                                          (int)R, 0, sort_end_bit(s->H, s->W), stream));
+        }
+        {
+            ProfScope _ps("tile_ranges_kernel", stream);
+            tile_ranges_kernel<<<cdiv(R, 256), 256, 0, stream>>>(R, b.keys, iv.ranges);
+        }
         GA_CHECK_LAUNCH("tile_ranges_kernel");
     }
     GeomViews g = carve_geom(geom, s->P);
-    render_fwd_kernel<<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, g.xy, g.conic_o,
-                                                                      colors, bg, iv.final_T, iv.n_contrib, out_color);
+    {
+        ProfScope _ps("render_fwd_kernel", stream);
+        render_fwd_kernel<<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, g.xy, g.conic_o,
+                                                                          colors, bg, iv.final_T, iv.n_contrib, out_color);
+    }
     GA_CHECK_LAUNCH("render_fwd_kernel");
     return GA_OK;
 }
@@ -727,15 +745,21 @@ extern "C" int ga_raster_backward(const GaRasterSettings *s, const float *means3
     if (R > 0) {
         GA_REQUIRE(binning, "NULL binning buffer");
         BinViews b = carve_bin(const_cast<void *>(binning), R, s->H, s->W);
-        render_bwd_kernel<<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, bg, g.xy,
-                                                                          g.conic_o, colors, iv.final_T, iv.n_contrib,
-                                                                          dL_dout, d_mean2D, d_conic_op, d_colors);
+        {
+            ProfScope _ps("render_bwd_kernel", stream);
+            render_bwd_kernel<<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, bg, g.xy,
+                                                                              g.conic_o, colors, iv.final_T, iv.n_contrib,
+                                                                              dL_dout, d_mean2D, d_conic_op, d_colors);
+        }
         GA_CHECK_LAUNCH("render_bwd_kernel");
     }
-    preprocess_bwd_kernel<<<cdiv(s->P, 256), 256, 0, stream>>>(s->P, s->H, s->W, s->tanfovx, s->tanfovy, s->scale_modifier,
-                                                              means3D, scales, rotations, viewmatrix, projmatrix, radii,
-                                                              g.cov3d, d_mean2D, d_conic_op, d_means3D, d_scales,
-                                                              d_rotations, d_opacities, d_means2D);
+    {
+        ProfScope _ps("preprocess_bwd_kernel", stream);
+        preprocess_bwd_kernel<<<cdiv(s->P, 256), 256, 0, stream>>>(s->P, s->H, s->W, s->tanfovx, s->tanfovy, s->scale_modifier,
+                                                                  means3D, scales, rotations, viewmatrix, projmatrix, radii,
+                                                                  g.cov3d, d_mean2D, d_conic_op, d_means3D, d_scales,
+                                                                  d_rotations, d_opacities, d_means2D);
+    }
     GA_CHECK_LAUNCH("preprocess_bwd_kernel");
     return GA_OK;
 }

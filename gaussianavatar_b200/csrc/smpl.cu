@@ -221,7 +221,7 @@ extern "C" int ga_smpl_forward(int32_t B, const float *pose, const float *transl
     GA_REQUIRE(B >= 0, "bad batch %d", B);
     if (B == 0) return GA_OK;
     GA_REQUIRE(pose && transl && rest_joints && inv_cano && cano2live && saved_G, "NULL pointer argument");
-    smpl_fwd_kernel<<<B, 32, 0, static_cast<cudaStream_t>(stream_)>>>(B, pose, transl, rest_joints, inv_cano, cano2live, saved_G);
+    { ProfScope _ps("smpl_fwd_kernel", static_cast<cudaStream_t>(stream_)); smpl_fwd_kernel<<<B, 32, 0, static_cast<cudaStream_t>(stream_)>>>(B, pose, transl, rest_joints, inv_cano, cano2live, saved_G); }
     GA_CHECK_LAUNCH("smpl_fwd_kernel");
     return GA_OK;
 }
@@ -232,7 +232,7 @@ extern "C" int ga_smpl_backward(int32_t B, const float *pose, const float *rest_
     GA_REQUIRE(B >= 0, "bad batch %d", B);
     if (B == 0) return GA_OK;
     GA_REQUIRE(pose && rest_joints && inv_cano && saved_G && d_cano2live && d_pose && d_transl, "NULL pointer argument");
-    smpl_bwd_kernel<<<B, 32, 0, static_cast<cudaStream_t>(stream_)>>>(B, pose, rest_joints, inv_cano, saved_G, d_cano2live, d_pose, d_transl);
+    { ProfScope _ps("smpl_bwd_kernel", static_cast<cudaStream_t>(stream_)); smpl_bwd_kernel<<<B, 32, 0, static_cast<cudaStream_t>(stream_)>>>(B, pose, rest_joints, inv_cano, saved_G, d_cano2live, d_pose, d_transl); }
     GA_CHECK_LAUNCH("smpl_bwd_kernel");
     return GA_OK;
 }

@@ -43,6 +43,10 @@ int ga_version(void);
 const char *ga_last_error(void);
 /* Number of kernels this library has launched in the calling process since load (bench.py's gpu_launches). */
 long long ga_launch_count(void);
+/* Optional per-kernel CUDA-event timing of this library's launches (bench.py roofline leg).  ga_profile_report
+ * synchronises the device and writes one "name count total_ms" line per kernel name, then clears the log. */
+void ga_profile_enable(int on);
+int ga_profile_report(char *buf, size_t cap);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Rasterizer.  Layout contracts: contiguous fp32; means3D [P,3]; colors [P,3] (colors_precomp);
@@ -156,6 +160,24 @@ int ga_decoder_forward(const GaDecoderDesc *d, const float *params, const float 
 int ga_decoder_backward(const GaDecoderDesc *d, const float *params, void *workspace, const float *dec_out,
                         const float *d_dec_out, float *d_params, float *d_geo_nchw, void *stream);
 int ga_decoder_views(const GaDecoderDesc *d, void *workspace, GaDecoderViews *out);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused image loss (utils/loss_utils.py:7-8,23-53 as combined at train.py:74-77):
+ *   out3[0] = w_l1 * mean|image - gt| + w_ssim * (1 - ssim(image, gt)),  out3[1] = ssim, out3[2] = l1   (device floats)
+ * image / gt [B,3,H,W].  The workspace (ga_loss_workspace_bytes) carries the SSIM partial-derivative maps from forward to
+ * backward.  grad_out: device scalar dL/d out3[0] (NULL = 1).  d_image is overwritten.
+ * ---------------------------------------------------------------------------------------------------------------- */
+size_t ga_loss_workspace_bytes(int32_t B, int32_t H, int32_t W);
+int ga_loss_forward(int32_t B, int32_t H, int32_t W, const float *image, const float *gt, float w_l1, float w_ssim,
+                    void *workspace, float *out3, void *stream);
+int ga_loss_backward(int32_t B, int32_t H, int32_t W, const float *image, const float *gt, float w_l1, float w_ssim,
+                     const float *grad_out, void *workspace, float *d_image, void *stream);
+
+/* torch.optim.Adam step (amsgrad=False, weight_decay=0; model/avatar_model.py:148-155,264-267) on one contiguous buffer.
+ * `step` is the 1-based count of this update; grad_scale multiplies the gradient first (1/world_size after an
+ * all-reduce(sum)). */
+int ga_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float lr, float beta1,
+                 float beta2, float eps, int64_t step, float grad_scale, void *stream);
 
 #ifdef __cplusplus
 }
