@@ -16,6 +16,8 @@
 #include "gemm.cuh"
 
 namespace ga {
+int launch_tc_fwd(const float *X, int ldx, int K, const float *a, const float *b, const float *W, int ldw, const float *bias, float *Y,
+                  int ldy, int accumulate, double *sum, double *sumsq, int M, cudaStream_t st);
 namespace {
 
 constexpr int kCg = 64;        // c_geom
@@ -532,6 +534,30 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
         GA_CHECK_LAUNCH("bn_finalize_fwd_kernel");
         return GA_OK;
     };
+    if (d->flags & GA_DECODER_TENSOR_CORES) {
+        // ---- tcgen05 / TF32 path: one persistent warp-specialised launch per 128-wide layer (mlp_tc.cu) ----
+        if (int rc = launch_tc_fwd(w.feat, kFeatLd, kFeatLd, nullptr, nullptr, params + L.w[0], kFeatLd, params + L.b[0], w.Y[0], kH, 0,
+                                   sum + kBnOff[0], sumsq + kBnOff[0], M, st)) return rc;
+        if (int rc = finalize(0, kH)) return rc;
+        for (int l = 1; l <= 3; ++l) {
+            if (int rc = launch_tc_fwd(w.Y[l - 1], kH, kH, cf.a + kBnOff[l - 1], cf.b + kBnOff[l - 1], params + L.w[l], kH, params + L.b[l], w.Y[l], kH,
+                                       0, sum + kBnOff[l], sumsq + kBnOff[l], M, st)) return rc;
+            if (int rc = finalize(l, kH)) return rc;
+        }
+        // layer 5 = feat part (K=72, raw) then the x4 part accumulating on top (K=128) + bias + statistics
+        if (int rc = launch_tc_fwd(w.feat, kFeatLd, kFeatLd, nullptr, nullptr, params + L.w[4], kK5, nullptr, w.Y[4], kH, 0, nullptr, nullptr, M, st)) return rc;
+        if (int rc = launch_tc_fwd(w.Y[3], kH, kH, cf.a + kBnOff[3], cf.b + kBnOff[3], params + L.w[4] + kFeatLd, kK5, params + L.b[4], w.Y[4], kH, 1,
+                                   sum + kBnOff[4], sumsq + kBnOff[4], M, st)) return rc;
+        if (int rc = finalize(4, kH)) return rc;
+        for (int h = 0; h < 3; ++h)
+            if (int rc = launch_tc_fwd(w.Y[4], kH, kH, cf.a + kBnOff[4], cf.b + kBnOff[4], params + L.w[5] + (size_t)h * kH * kH, kH,
+                                       params + L.b[5] + h * kH, w.Y6 + h * kH, 3 * kH, 0, sum + kBnOff[5] + h * kH, sumsq + kBnOff[5] + h * kH, M, st)) return rc;
+        if (int rc = finalize(5, 3 * kH)) return rc;
+        for (int h = 0; h < 3; ++h)
+            if (int rc = launch_tc_fwd(w.Y6 + h * kH, 3 * kH, kH, cf.a + kBnOff[5] + h * kH, cf.b + kBnOff[5] + h * kH,
+                                       params + L.w[6] + (size_t)h * kH * kH, kH, params + L.b[6] + h * kH, w.Y7 + h * kH, 3 * kH, 0,
+                                       sum + kBnOff[6] + h * kH, sumsq + kBnOff[6] + h * kH, M, st)) return rc;
+    } else {
     // layer 1: feat (raw) -> Y1
     {
         ALoadConcatActK<128> A{w.feat, kFeatLd, kFeatLd, nullptr, 0, ChanAffine{nullptr, nullptr}, M, kFeatLd};
@@ -566,6 +592,7 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
         BLoadWT<128> B{params + L.w[6] + (size_t)h * kH * kH, kH, kH, kH};
         EpiStoreStats E{w.Y7 + h * kH, 3 * kH, M, kH, params + L.b[6] + h * kH, sum + kBnOff[6] + h * kH, sumsq + kBnOff[6] + h * kH, false};
         if (int rc = launch_gemm<128, 128>("mlp_fwd_l7", A, B, E, M, kH, kH, 1, st)) return rc;
+    }
     }
     if (int rc = finalize(6, 3 * kH)) return rc;
     {

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -25,8 +26,9 @@ _BN_LAYERS = ["bn1", "bn2", "bn3", "bn4", "bn5", "bn6", "bn6N", "bn6SH", "bn7", 
 class DecoderState:
     """Device-side state of one decoder instance: descriptor, activation workspace, BatchNorm running statistics."""
 
-    def __init__(self, S: int, feat_res: int, batch: int, device, c_geom=64, hsize=128, eps=1e-5, momentum=0.1):
-        self.desc = _lib.GaDecoderDesc(int(S), int(feat_res), int(batch), int(c_geom), int(hsize), float(eps), float(momentum))
+    def __init__(self, S: int, feat_res: int, batch: int, device, c_geom=64, hsize=128, eps=1e-5, momentum=0.1, tensor_cores=True):
+        self.desc = _lib.GaDecoderDesc(int(S), int(feat_res), int(batch), int(c_geom), int(hsize), float(eps), float(momentum),
+                                       1 if tensor_cores else 0)
         nbytes = _lib.lib().ga_decoder_workspace_bytes(ctypes.byref(self.desc))
         if nbytes == 0:
             raise RuntimeError("ga_decoder_workspace_bytes failed: " + _lib.lib().ga_last_error().decode())
@@ -37,7 +39,7 @@ class DecoderState:
 
 
 def decoder_layout(c_geom=64, hsize=128) -> _lib.GaDecoderLayout:
-    desc = _lib.GaDecoderDesc(2, 1, 1, c_geom, hsize, 1e-5, 0.1)
+    desc = _lib.GaDecoderDesc(2, 1, 1, c_geom, hsize, 1e-5, 0.1, 0)
     lay = _lib.GaDecoderLayout()
     _lib.check(_lib.lib().ga_decoder_layout(ctypes.byref(desc), ctypes.byref(lay)), "ga_decoder_layout")
     return lay
@@ -54,6 +56,8 @@ class POP_no_unet(nn.Module):
             raise NotImplementedError("only c_geom=64, hsize=128, uv_feat_dim=2 (arguments/__init__.py:101-111) are built")
         self.geom_layer_type = geom_layer_type
         self.c_geom, self.hsize = c_geom, hsize
+        # MLP math: tcgen05 TF32 tensor cores (what the reference's cuDNN convs use on Ampere+) or strict FP32 CUDA cores
+        self.tensor_cores = os.environ.get("GA_DECODER_FP32", "0") != "1"
         self.layout = decoder_layout(c_geom, hsize)
         self.flat = nn.Parameter(torch.zeros(int(self.layout.total)))
         self.register_buffer("bn_running", torch.cat([torch.zeros(self.layout.bn_channels), torch.ones(self.layout.bn_channels)]).reshape(2, -1))
@@ -169,10 +173,10 @@ class POP_no_unet(nn.Module):
 
     # ---- execution ------------------------------------------------------------------------------------------------
     def _state(self, S, feat_res, batch) -> DecoderState:
-        key = (int(S), int(feat_res), int(batch), self.flat.device)
+        key = (int(S), int(feat_res), int(batch), self.flat.device, bool(self.tensor_cores))
         st = self._states.get(key)
         if st is None:
-            st = DecoderState(S, feat_res, batch, self.flat.device, self.c_geom, self.hsize)
+            st = DecoderState(S, feat_res, batch, self.flat.device, self.c_geom, self.hsize, tensor_cores=self.tensor_cores)
             self._states[key] = st
         st.bn_running = self.bn_running
         st.track_running = True     # the reference never calls .eval(): BatchNorm always uses batch statistics

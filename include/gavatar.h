@@ -143,7 +143,9 @@ int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float scale_mul, c
 typedef struct GaDecoderDesc {
     int32_t S, feat_res, batch, c_geom, hsize;
     float bn_eps, bn_momentum;
+    int32_t flags;   /* GA_DECODER_TENSOR_CORES: MLP layers on tcgen05 (TF32, the reference's cuDNN numerics); 0: strict FP32 */
 } GaDecoderDesc;
+#define GA_DECODER_TENSOR_CORES 1
 typedef struct GaDecoderLayout {
     int64_t gconv[3];
     int64_t w[7], b[7], gamma[7], beta[7];
@@ -160,6 +162,12 @@ int ga_decoder_forward(const GaDecoderDesc *d, const float *params, const float 
 int ga_decoder_backward(const GaDecoderDesc *d, const float *params, void *workspace, const float *dec_out,
                         const float *d_dec_out, float *d_params, float *d_geo_nchw, void *stream);
 int ga_decoder_views(const GaDecoderDesc *d, void *workspace, GaDecoderViews *out);
+/* One decoder layer on the tensor cores (building block of ga_decoder_forward, exposed for unit tests):
+ * Y[M,128] (+)= softplus(X * bn_a + bn_b)[M,K] W[128,K]^T + bias (bn_a == NULL: X used raw); optional per-column
+ * sum / sum-of-squares accumulation (double[128]).  K % 8 == 0, K <= 128; ld* % 4 == 0. */
+int ga_tc_linear_forward(int32_t M, int32_t K, const float *X, int32_t ldx, const float *bn_a, const float *bn_b, const float *W,
+                         int32_t ldw, const float *bias, float *Y, int32_t ldy, int32_t accumulate, double *sum, double *sumsq,
+                         void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Fused image loss (utils/loss_utils.py:7-8,23-53 as combined at train.py:74-77):

@@ -1,0 +1,69 @@
+"""GPU: the tcgen05 (TF32) decoder layer against fp64 torch math, and the whole TF32 decoder against the reference fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def tc_linear(X, W, bias=None, a=None, b=None, Y0=None, stats=True):
+    from gaussianavatar_b200 import _lib
+    from gaussianavatar_b200._lib import ptr
+    M, K = X.shape[0], W.shape[1]
+    Y = Y0.clone() if Y0 is not None else torch.empty(M, 128, device=DEV)
+    s = torch.zeros(2, 128, dtype=torch.float64, device=DEV) if stats else None
+    _lib.check(_lib.lib().ga_tc_linear_forward(M, K, ptr(X), X.stride(0), ptr(a), ptr(b), ptr(W), W.stride(0), ptr(bias), ptr(Y), Y.stride(0),
+                                               1 if Y0 is not None else 0, ptr(s[0]) if stats else None, ptr(s[1]) if stats else None,
+                                               torch.cuda.current_stream().cuda_stream), "ga_tc_linear_forward")
+    torch.cuda.synchronize()
+    return Y, s
+
+
+def tf32_trunc(t):
+    return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,K,act,acc", [(128, 128, False, False), (1024, 128, True, False), (5000, 72, False, False),
+                                         (128 * 300, 128, True, True), (2304, 128, True, False)])
+def test_tc_linear_forward(M, K, act, acc):
+    g = torch.Generator().manual_seed(M + K)
+    X = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(128, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(128, generator=g).to(DEV)
+    a = (1 + 0.2 * torch.randn(K, generator=g)).to(DEV) if act else None
+    b = (0.3 * torch.randn(K, generator=g)).to(DEV) if act else None
+    Y0 = torch.randn(M, 128, generator=g).to(DEV) if acc else None
+    Y, s = tc_linear(X, W, bias, a, b, Y0)
+    Xa = torch.nn.functional.softplus(X * a + b) if act else X
+    ref = Xa.double() @ W.double().t() + bias.double() + (Y0.double() if acc else 0)
+    # TF32: 10-bit mantissas on both operands -> ~1e-3 relative on a K-term dot product of O(1) values
+    err = (Y.double() - ref).abs().max().item()
+    assert err < 6e-3 * max(1.0, ref.abs().max().item()), err
+    # tight check against fp64 math on TF32-truncated operands (isolates layout / descriptor bugs from rounding)
+    ref_t = tf32_trunc(Xa).double() @ tf32_trunc(W).double().t() + bias.double() + (Y0.double() if acc else 0)
+    assert (Y.double() - ref_t).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item())
+    assert (s[0] - Y.double().sum(0)).abs().max().item() < 1e-3 * M ** 0.5
+    assert (s[1] - (Y.double() ** 2).sum(0)).abs().max().item() < 1e-3 * M
+
+
+@pytest.mark.parametrize("name", ["pop_s32_in16.npz", "pop_s48_in128.npz"])
+def test_decoder_tf32_forward_vs_reference_fixture(name):
+    """TF32 tensor-core forward vs the reference's CPU fp32 outputs: tolerance per SURVEY App. C (rel-L2 <= 2e-3)."""
+    from gaussianavatar_b200.network import POP_no_unet
+    from oracle import avatar_oracle as ao
+    d = np.load(os.path.join(GOLD, name))
+    inp, S, B, seed = int(d["inp"]), int(d["S"]), int(d["B"]), int(d["seed"])
+    net = POP_no_unet(c_geom=64, hsize=128).to(DEV)
+    assert net.tensor_cores
+    net.load_state_dict(ao.seeded_pop_params(seed), strict=False)
+    g = torch.Generator().manual_seed(seed + 1)
+    geo = (torch.randn(1, 64, inp, inp, generator=g) * 0.01).to(DEV)
+    dec = net.forward_packed(geo, S, B).detach().cpu().numpy()
+    for sl, key in ((slice(0, 3), "res"), (slice(3, 4), "scales"), (slice(4, 7), "shs")):
+        ref = d[key][0].T
+        rel = np.linalg.norm(dec[:, sl] - ref) / np.linalg.norm(ref)
+        assert rel < 2e-3, (key, rel)

@@ -128,5 +128,6 @@ def test_train_step_gradients_vs_oracle_chain():
     before = m.net.flat.detach().clone()
     tr.sync_gradients(); m.optimizer.grad_scale = 1.0; m.step(1)
     delta = (m.net.flat.detach() - before)
-    nz = m.net.flat.grad.abs() > 1e-7
-    assert torch.allclose(delta[nz].abs(), torch.full_like(delta[nz], 3e-3), rtol=1e-3)
+    nz = m.net.flat.grad.abs() > 1e-4      # well above Adam's eps = 1e-8
+    assert torch.allclose(delta[nz].abs(), torch.full_like(delta[nz], 3e-3), rtol=2e-3)
+    assert torch.equal(torch.sign(delta[nz]), -torch.sign(m.net.flat.grad[nz]))
