@@ -16,6 +16,9 @@
 #include "gemm.cuh"
 
 namespace ga {
+int launch_tc_bwd(const float *dZ, const float *Y, int ldg, const float *ga, const float *m1, const float *m2, const float *mu, const float *rstd,
+                  const float *Yprev, int ldp, const float *pa, const float *pb, const float *pmu, const float *prstd, const float *W, int ldw,
+                  float *dW, int lddw, float *dZprev, int ldo, int mode, double *s1, double *s2, int M, cudaStream_t st);
 int launch_tc_fwd(const float *X, int ldx, int K, const float *a, const float *b, const float *W, int ldw, const float *bias, float *Y,
                   int ldy, int accumulate, double *sum, double *sumsq, int M, cudaStream_t st);
 namespace {
@@ -655,6 +658,42 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         GA_CHECK_LAUNCH("heads_bwd_kernel<2>");
         if (int rc = finalize(6, 3 * kH)) return rc;
     }
+    float *cur = nullptr, *nxt = nullptr;
+    if (d->flags & GA_DECODER_TENSOR_CORES) {
+        // ---- tcgen05 / TF32 path: data + weight gradient of a layer in one fused launch (mlp_tc.cu: tc_bwd_kernel) ----
+        auto tc = [&](const float *dZl, const float *Yl, int ldg, int ol, const float *Yp, int ldp, int op, const float *Wl, int ldw, float *dWl,
+                      float *dZp, int ldo, int mode) -> int {
+            return launch_tc_bwd(dZl, Yl, ldg, cf.ga + ol, cf.m1 + ol, cf.m2 + ol, cf.mean + ol, cf.rstd + ol, Yp, ldp, cf.a + op, cf.b + op,
+                                 cf.mean + op, cf.rstd + op, Wl, ldw, dWl, ldw, dZp, ldo, mode, s1 + op, s2 + op, M, st);
+        };
+        for (int h = 0; h < 3; ++h)      // layer 7 heads -> dZ6[:, h]
+            if (int rc = tc(w.dZ7 + h * kH, w.Y7 + h * kH, 3 * kH, kBnOff[6] + h * kH, w.Y6 + h * kH, 3 * kH, kBnOff[5] + h * kH,
+                            params + L.w[6] + (size_t)h * kH * kH, kH, d_params + L.w[6] + (size_t)h * kH * kH, w.dZ6 + h * kH, 3 * kH, 0)) return rc;
+        if (int rc = finalize(5, 3 * kH)) return rc;
+        for (int h = 0; h < 3; ++h)      // layer 6 heads all feed x5: raw partial sums, activation backward on the last one
+            if (int rc = tc(w.dZ6 + h * kH, w.Y6 + h * kH, 3 * kH, kBnOff[5] + h * kH, w.Y[4], kH, kBnOff[4], params + L.w[5] + (size_t)h * kH * kH, kH,
+                            d_params + L.w[5] + (size_t)h * kH * kH, w.dZa, kH, h == 0 ? 1 : (h == 1 ? 2 : 3))) return rc;
+        if (int rc = finalize(4, kH)) return rc;
+        {   // layer 5: x4 part on the tensor cores, the 72-wide feature part on the CUDA cores
+            const int o5 = kBnOff[4];
+            if (int rc = tc(w.dZa, w.Y[4], kH, o5, w.Y[3], kH, kBnOff[3], params + L.w[4] + kFeatLd, kK5, d_params + L.w[4] + kFeatLd, w.dZb, kH, 0)) return rc;
+            ALoadBnBwdD<128> A{w.dZa, w.Y[4], kH, bwdcoef(o5), kH, M};
+            BLoadConcatActD<128> B{w.feat, kFeatLd, kFeatLd, nullptr, 0, ChanAffine{nullptr, nullptr}, kFeatLd, M};
+            EpiAtomicAdd E{d_params + L.w[4], kK5, kH, kFeatLd};
+            if (int rc = launch_gemm<128, 128>("mlp_wgrad_l5_feat", A, B, E, kH, kFeatLd, M, kSplit, st)) return rc;
+            ALoadBnBwdK<128> A2{w.dZa, w.Y[4], kH, bwdcoef(o5), M, kH};
+            BLoadDirect<128> B2{params + L.w[4], kK5, kFeatLd, kH};
+            EpiDgradAct E2{M, kFeatLd, kFeatLd, w.d_feat, kFeatLd, false, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            if (int rc = launch_gemm<128, 128>("mlp_dgrad_l5_feat", A2, B2, E2, M, kFeatLd, kH, 1, st)) return rc;
+            if (int rc = finalize(3, kH)) return rc;
+        }
+        cur = w.dZb; nxt = w.dZa;
+        for (int l = 3; l >= 1; --l) {
+            if (int rc = tc(cur, w.Y[l], kH, kBnOff[l], w.Y[l - 1], kH, kBnOff[l - 1], params + L.w[l], kH, d_params + L.w[l], nxt, kH, 0)) return rc;
+            if (int rc = finalize(l - 1, kH)) return rc;
+            float *t = cur; cur = nxt; nxt = t;
+        }
+    } else {
     // layer 7 (per head): wgrad, then dgrad -> dZ6
     for (int h = 0; h < 3; ++h) {
         const int o7 = kBnOff[6] + h * kH, o6 = kBnOff[5] + h * kH;
@@ -699,7 +738,7 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         if (int rc = finalize(3, kH)) return rc;
     }
     // layers 4, 3, 2: dZ_l alternates dZb -> dZa -> dZb -> dZa
-    float *cur = w.dZb, *nxt = w.dZa;
+    cur = w.dZb; nxt = w.dZa;
     for (int l = 3; l >= 1; --l) {
         const int ol = kBnOff[l], op = kBnOff[l - 1];
         ALoadBnBwdD<128> A{cur, w.Y[l], kH, bwdcoef(ol), kH, M};
@@ -712,6 +751,7 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         if (int rc = launch_gemm<128, 128>("mlp_dgrad_l2_4", A2, B2, E2, M, kH, kH, 1, st)) return rc;
         if (int rc = finalize(l - 1, kH)) return rc;
         float *t = cur; cur = nxt; nxt = t;
+    }
     }
     // layer 1: cur = dZ1
     {

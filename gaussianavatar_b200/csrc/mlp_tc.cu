@@ -71,7 +71,7 @@ tc_fwd_kernel(const TcFwdParams p)
     for (int i = tid; i < kBN * (p.K / 4); i += kTcThreads) {
         const int n = i / (p.K / 4), q = i % (p.K / 4);
         const float4 v = *reinterpret_cast<const float4 *>(p.W + (size_t)n * p.ldw + q * 4);
-        *reinterpret_cast<float4 *>(sm.w + (q >> 3) * kChunkBytes + sw128_offset(n, q & 7)) = v;
+        *reinterpret_cast<float4 *>(sm.w + (q >> 3) * kChunkBytes + sw128_offset(n, q & 7)) = to_tf32(v);
     }
     for (int i = tid; i < kBN; i += kTcThreads) {
         sm.sbias[i] = p.bias ? p.bias[i] : 0.f;
@@ -114,7 +114,7 @@ tc_fwd_kernel(const TcFwdParams p)
                             x.x = softplus_f(fmaf(x.x, av.x, bv.x)); x.y = softplus_f(fmaf(x.y, av.y, bv.y));
                             x.z = softplus_f(fmaf(x.z, av.z, bv.z)); x.w = softplus_f(fmaf(x.w, av.w, bv.w));
                         }
-                        *reinterpret_cast<float4 *>(dst + c * kChunkBytes + sw128_offset(r, u)) = x;
+                        *reinterpret_cast<float4 *>(dst + c * kChunkBytes + sw128_offset(r, u)) = to_tf32(x);
                     }
                 }
             }
@@ -238,4 +238,272 @@ extern "C" int ga_tc_linear_forward(int32_t M, int32_t K, const float *X, int32_
 {
     GA_REQUIRE(M > 0 && X && W && Y, "bad arguments");
     return ga::launch_tc_fwd(X, ldx, K, bn_a, bn_b, W, ldw, bias, Y, ldy, accumulate, sum, sumsq, M, static_cast<cudaStream_t>(stream));
+}
+
+// =====================================================================================================================
+// Backward of one hidden layer on the tensor cores: data gradient AND weight gradient from ONE pass over the tile.
+//
+//   G  = dY_l      [px, out] = ga (dZ_l - m1 - xhat_l m2)          BatchNorm backward applied while loading (dZ_l, Y_l)
+//   X  = x_l       [px, in ] = softplus(a Y_{l-1} + b)             recomputed while loading Y_{l-1}
+//   dW_l [out,in] += G^T X      tcgen05.mma, A = G and B = X as MN-major operands; accumulator lives in TMEM for the
+//                               whole kernel (one flush per CTA at the end)
+//   dX^T [in, px]  = W_l^T G^T  tcgen05.mma, A = W_l as MN-major, B = G as K-major; computed TRANSPOSED so that a TMEM
+//                               lane is an input channel: the epilogue thread's BatchNorm scalars are constants and the
+//                               per-channel statistics sum(dZ), sum(dZ xhat) need no cross-thread reduction
+//   dZ_{l-1} = dX * sigmoid(z_{l-1})   (z_{l-1}, xhat_{l-1} from a coalesced, L2-hot re-read of Y_{l-1})
+// The SAME 128-byte-swizzled [pixel row][32-channel chunk] shared-memory tile is a K-major operand in one product and
+// an MN-major operand in the other (tc_common.cuh), so G and X are staged exactly once.
+// 64-pixel tiles, two stages, 13 warps: 4 producers for G, 4 for X, 1 MMA issuer, 4 epilogue.
+// =====================================================================================================================
+namespace ga {
+namespace {
+
+constexpr int kPx = 64;
+constexpr int kBChunk = kPx * 128;        // 8 KB: 32 channels x 64 pixel rows
+constexpr int kBTile = 4 * kBChunk;       // 32 KB
+constexpr int kBwdThreads = 13 * 32;
+constexpr uint32_t kBwdTmemCols = 256;    // [0,128): dW accumulator; 128 + 64 s: dX^T accumulator of stage s
+
+struct TcBwdParams {
+    const float *dZ, *Y; int ldg;                      // layer l: [M][ldg], 128 output channels from the pointer
+    const float *ga, *m1, *m2, *mu, *rstd;             // BatchNorm backward of layer l (ga == nullptr: G = dZ)
+    const float *Yprev; int ldp;                       // layer l-1 pre-BN output, 128 channels
+    const float *pa, *pb, *pmu, *prstd;                // BatchNorm (folded) of layer l-1
+    const float *W; int ldw;                           // [128 out][128 in]
+    float *dW; int lddw;                               // += (atomics)
+    float *dZprev; int ldo;
+    int mode;                                          // 0 final, 1 store raw dX, 2 accumulate raw dX, 3 final on (existing + dX)
+    double *s1, *s2;
+    int M;
+};
+
+struct alignas(1024) TcBwdSmem {
+    unsigned char w[4 * kBM * 128];                    // 64 KB, rows = out channel
+    unsigned char g[2][kBTile];
+    unsigned char x[2][kBTile];
+    float ga[128], m1[128], m2[128], mu[128], rstd[128], pa[128], pb[128], pmu[128], prstd[128];
+    uint64_t full[2], empty[2], mma_done[2], tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+tc_bwd_kernel(const TcBwdParams p)
+{
+    extern __shared__ unsigned char smem_raw[];
+    TcBwdSmem &sm = *reinterpret_cast<TcBwdSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int num_tiles = (p.M + kPx - 1) / kPx;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&sm.full[s], 256); mbar_init(&sm.empty[s], 128);
+            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 8) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
+    for (int i = tid; i < 128 * 32; i += kBwdThreads) {
+        const int n = i >> 5, q = i & 31;
+        const float4 v = *reinterpret_cast<const float4 *>(p.W + (size_t)n * p.ldw + q * 4);
+        *reinterpret_cast<float4 *>(sm.w + (q >> 3) * (kBM * 128) + sw128_offset(n, q & 7)) = to_tf32(v);
+    }
+    for (int i = tid; i < 128; i += kBwdThreads) {
+        sm.ga[i] = p.ga ? p.ga[i] : 1.f; sm.m1[i] = p.ga ? p.m1[i] : 0.f; sm.m2[i] = p.ga ? p.m2[i] : 0.f;
+        sm.mu[i] = p.ga ? p.mu[i] : 0.f; sm.rstd[i] = p.ga ? p.rstd[i] : 0.f;
+        sm.pa[i] = p.pa[i]; sm.pb[i] = p.pb[i]; sm.pmu[i] = p.pmu[i]; sm.prstd[i] = p.prstd[i];
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp < 8) {
+        // ================================ producers: warps 0-3 build G, warps 4-7 build X ================================
+        const bool isG = warp < 4;
+        const int pw = warp & 3, rl = lane >> 3, u = lane & 7;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int s = it & 1, n = it >> 1;
+            mbar_wait(&sm.empty[s], (n & 1) ^ 1);
+            unsigned char *dst = isG ? sm.g[s] : sm.x[s];
+            const int m0 = tile * kPx;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int k = c * 32 + u * 4;
+                if (isG) {
+                    float4 dz[4], yy[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int m = m0 + j * 16 + pw * 4 + rl;
+                        const bool ok = m < p.M;
+                        dz[j] = ok ? *reinterpret_cast<const float4 *>(p.dZ + (size_t)m * p.ldg + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        yy[j] = (ok && p.ga) ? *reinterpret_cast<const float4 *>(p.Y + (size_t)m * p.ldg + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    const float4 ga = *reinterpret_cast<const float4 *>(&sm.ga[k]), m1 = *reinterpret_cast<const float4 *>(&sm.m1[k]),
+                                 m2 = *reinterpret_cast<const float4 *>(&sm.m2[k]), mu = *reinterpret_cast<const float4 *>(&sm.mu[k]),
+                                 rs = *reinterpret_cast<const float4 *>(&sm.rstd[k]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = j * 16 + pw * 4 + rl;
+                        float4 gq;
+                        gq.x = ga.x * (dz[j].x - m1.x - (yy[j].x - mu.x) * rs.x * m2.x);
+                        gq.y = ga.y * (dz[j].y - m1.y - (yy[j].y - mu.y) * rs.y * m2.y);
+                        gq.z = ga.z * (dz[j].z - m1.z - (yy[j].z - mu.z) * rs.z * m2.z);
+                        gq.w = ga.w * (dz[j].w - m1.w - (yy[j].w - mu.w) * rs.w * m2.w);
+                        if (m0 + r >= p.M) gq = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4 *>(dst + c * kBChunk + sw128_offset(r, u)) = to_tf32(gq);
+                    }
+                } else {
+                    float4 yy[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int m = m0 + j * 16 + pw * 4 + rl;
+                        yy[j] = (m < p.M) ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[k]), bv = *reinterpret_cast<const float4 *>(&sm.pb[k]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = j * 16 + pw * 4 + rl;
+                        float4 x;
+                        x.x = softplus_f(fmaf(yy[j].x, av.x, bv.x)); x.y = softplus_f(fmaf(yy[j].y, av.y, bv.y));
+                        x.z = softplus_f(fmaf(yy[j].z, av.z, bv.z)); x.w = softplus_f(fmaf(yy[j].w, av.w, bv.w));
+                        if (m0 + r >= p.M) x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        *reinterpret_cast<float4 *>(dst + c * kBChunk + sw128_offset(r, u)) = to_tf32(x);
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&sm.full[s]);
+        }
+    } else if (warp == 8) {
+        // ================================ MMA issuer ================================
+        constexpr uint32_t idesc_dgrad = make_idesc_tf32(128, kPx, /*A MN-major*/ true, /*B K-major*/ false);
+        constexpr uint32_t idesc_wgrad = make_idesc_tf32(128, 128, true, true);
+        const uint32_t w_addr = smem_u32(sm.w);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int s = it & 1, n = it >> 1;
+            mbar_wait(&sm.full[s], n & 1);
+            mbar_wait(&sm.tmem_empty[s], (n & 1) ^ 1);
+            tc_fence_after_sync();
+            if (lane == 0) {
+                const uint32_t g_addr = smem_u32(sm.g[s]), x_addr = smem_u32(sm.x[s]);
+                // dX^T[in, px] = sum_out W[out, in] G[px, out]: 16 steps of 8 output channels
+#pragma unroll 1
+                for (int k = 0; k < 16; ++k)
+                    mma_tf32(tmem_base + 128 + (uint32_t)s * kPx, make_smem_desc(w_addr + k * 1024, kBM * 128, 1024),
+                             make_smem_desc(g_addr + (k >> 2) * kBChunk + (k & 3) * 32, 16, 1024), idesc_dgrad, k > 0);
+                // dW[out, in] += sum_px G[px, out] X[px, in]: 8 steps of 8 pixels
+#pragma unroll 1
+                for (int j = 0; j < kPx / 8; ++j)
+                    mma_tf32(tmem_base, make_smem_desc(g_addr + j * 1024, kBChunk, 1024), make_smem_desc(x_addr + j * 1024, kBChunk, 1024),
+                             idesc_wgrad, (it > 0) || (j > 0));
+                mma_commit(&sm.mma_done[s]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================================ epilogue: one input channel per thread ================================
+        const int q = warp & 3;
+        const int c = q * 32 + lane;                 // TMEM lane == input channel
+        const int we = warp - 9;                     // 0..3 for the coalesced store phase
+        const float ca = sm.pa[c], cb = sm.pb[c], cmu = sm.pmu[c], crs = sm.prstd[c];
+        const bool final_mode = (p.mode == 0 || p.mode == 3);
+        double d1 = 0.0, d2 = 0.0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const int s = it & 1, n = it >> 1;
+            const int m0 = tile * kPx;
+            mbar_wait(&sm.mma_done[s], n & 1);
+            tc_fence_after_sync();
+            float *stg = reinterpret_cast<float *>(sm.g[s]);       // both products have consumed G[s]: reuse as [px][128] staging
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+            for (int hh = 0; hh < 2; ++hh) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx + hh * 32, v);
+                float yv[32], ev[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int m = m0 + hh * 32 + j;
+                    yv[j] = (final_mode && m < p.M) ? p.Yprev[(size_t)m * p.ldp + c] : 0.f;
+                    ev[j] = (p.mode >= 2 && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float dx = v[j] + ev[j];
+                    if (final_mode) {
+                        const float z = fmaf(yv[j], ca, cb);
+                        dx *= sigmoid_f(z);
+                        if (m0 + hh * 32 + j < p.M) { t1 += dx; t2 = fmaf(dx, (yv[j] - cmu) * crs, t2); }
+                    }
+                    stg[(hh * 32 + j) * 128 + c] = dx;
+                }
+            }
+            d1 += (double)t1; d2 += (double)t2;
+            tc_fence_before_sync();
+            mbar_arrive(&sm.tmem_empty[s]);
+            named_bar_sync(1, 128);
+            for (int r = we * 16; r < we * 16 + 16; ++r) {
+                const int m = m0 + r;
+                if (m >= p.M) break;
+                *reinterpret_cast<float4 *>(p.dZprev + (size_t)m * p.ldo + lane * 4) = *reinterpret_cast<const float4 *>(stg + r * 128 + lane * 4);
+            }
+            mbar_arrive(&sm.empty[s]);
+        }
+        if (final_mode && p.s1) { atomicAdd(&p.s1[c], d1); atomicAdd(&p.s2[c], d2); }
+        // flush the weight-gradient accumulator: lane == output channel; every MMA was covered by the last mma_done wait
+        tc_fence_after_sync();
+        {
+            const int o = c;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(p.dW + (size_t)o * p.lddw + cc * 32 + j, v[j]);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, kBwdTmemCols);
+}
+
+}  // namespace
+
+int launch_tc_bwd(const float *dZ, const float *Y, int ldg, const float *ga, const float *m1, const float *m2, const float *mu, const float *rstd,
+                  const float *Yprev, int ldp, const float *pa, const float *pb, const float *pmu, const float *prstd, const float *W, int ldw,
+                  float *dW, int lddw, float *dZprev, int ldo, int mode, double *s1, double *s2, int M, cudaStream_t st)
+{
+    GA_REQUIRE(ldg % 4 == 0 && ldp % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0, "tcgen05 backward: leading dimensions must be multiples of 4");
+    static bool attr_set = false;
+    if (!attr_set) {
+        GA_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcBwdSmem) + 1024));
+        attr_set = true;
+    }
+    TcBwdParams p{dZ, Y, ldg, ga, m1, m2, mu, rstd, Yprev, ldp, pa, pb, pmu, prstd, W, ldw, dW, lddw, dZprev, ldo, mode, s1, s2, M};
+    const int tiles = cdiv(M, kPx);
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    {
+        ProfScope _ps("mlp_tc_bwd", st);
+        tc_bwd_kernel<<<grid, kBwdThreads, sizeof(TcBwdSmem) + 1024, st>>>(p);
+    }
+    GA_CHECK_LAUNCH("tc_bwd_kernel");
+    return GA_OK;
+}
+
+}  // namespace ga
+
+// Unit-test / building-block entry for the fused backward layer (see tc_bwd_kernel).
+extern "C" int ga_tc_linear_backward(int32_t M, const float *dZ, const float *Y, int32_t ldg, const float *bwd_coef /*[5][128] ga,m1,m2,mu,rstd or NULL*/,
+                                     const float *Yprev, int32_t ldp, const float *prev_coef /*[4][128] a,b,mu,rstd*/, const float *W, int32_t ldw,
+                                     float *dW, int32_t lddw, float *dZprev, int32_t ldo, int32_t mode, double *s1, double *s2, void *stream)
+{
+    GA_REQUIRE(M > 0 && dZ && Yprev && prev_coef && W && dW && dZprev, "bad arguments");
+    const float *bc = bwd_coef;
+    return ga::launch_tc_bwd(dZ, Y, ldg, bc, bc ? bc + 128 : nullptr, bc ? bc + 256 : nullptr, bc ? bc + 384 : nullptr, bc ? bc + 512 : nullptr, Yprev,
+                             ldp, prev_coef, prev_coef + 128, prev_coef + 256, prev_coef + 384, W, ldw, dW, lddw, dZprev, ldo, mode, s1, s2, M,
+                             static_cast<cudaStream_t>(stream));
 }

@@ -87,6 +87,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32])
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// fp32 -> tf32 with round-to-nearest (the tensor core itself would truncate the low 13 mantissa bits)
+__device__ __forceinline__ float to_tf32(float x)
+{
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 to_tf32(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
+
 // ---- descriptors -----------------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle (LayoutType::SWIZZLE_128B = 2), version 1 (Blackwell).
 //   K-major  operand: rows of 128 B (32 fp32 of K), 8-row swizzle atoms 1024 B apart            -> SBO = 1024 B, LBO unused (1)

@@ -187,6 +187,15 @@ int ga_loss_backward(int32_t B, int32_t H, int32_t W, const float *image, const 
 int ga_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float lr, float beta1,
                  float beta2, float eps, int64_t step, float grad_scale, void *stream);
 
+/* Fused backward of one hidden decoder layer on the tensor cores (building block of ga_decoder_backward, exposed for unit
+ * tests): from dZ_l / Y_l (BatchNorm backward applied on load with bwd_coef = [ga, m1, m2, mu, rstd] x 128, NULL: dY = dZ)
+ * and Y_{l-1} (x = softplus(a y + b), prev_coef = [a, b, mu, rstd] x 128):  dW[128,128] += dY^T x  and
+ * dZprev = (dY W) * sigmoid(z_{l-1}) with per-channel sums s1 = sum dZprev, s2 = sum dZprev * xhat_{l-1} (double[128]).
+ * mode 0: as described; 1: store raw dY W; 2: dZprev += raw; 3: dZprev = (dZprev + dY W) * sigmoid, with statistics. */
+int ga_tc_linear_backward(int32_t M, const float *dZ, const float *Y, int32_t ldg, const float *bwd_coef, const float *Yprev, int32_t ldp,
+                          const float *prev_coef, const float *W, int32_t ldw, float *dW, int32_t lddw, float *dZprev, int32_t ldo,
+                          int32_t mode, double *s1, double *s2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
