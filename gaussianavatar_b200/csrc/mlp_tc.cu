@@ -245,24 +245,27 @@ extern "C" int ga_tc_linear_forward(int32_t M, int32_t K, const float *X, int32_
 //
 //   G  = dY_l      [px, out] = ga (dZ_l - m1 - xhat_l m2)          BatchNorm backward applied while loading (dZ_l, Y_l)
 //   X  = x_l       [px, in ] = softplus(a Y_{l-1} + b)             recomputed while loading Y_{l-1}
-//   dW_l [out,in] += G^T X      tcgen05.mma, A = G and B = X as MN-major operands; accumulator lives in TMEM for the
-//                               whole kernel (one flush per CTA at the end)
-//   dX^T [in, px]  = W_l^T G^T  tcgen05.mma, A = W_l as MN-major, B = G as K-major; computed TRANSPOSED so that a TMEM
-//                               lane is an input channel: the epilogue thread's BatchNorm scalars are constants and the
-//                               per-channel statistics sum(dZ), sum(dZ xhat) need no cross-thread reduction
+//   dW_l [out,in] += G^T X      A = G^T [out rows][px], B = X^T [in rows][px]  (both K-major: the producers write the
+//                               TRANSPOSED tiles); the accumulator lives in TMEM for the whole kernel, one flush at the end
+//   dX^T [in, px]  = W_l^T G^T  A = W_l^T [in rows][out] (transposed once per CTA), B = G [px rows][out]; computed
+//                               TRANSPOSED so that a TMEM lane is an input channel: the epilogue thread's BatchNorm
+//                               scalars are constants and sum(dZ), sum(dZ xhat) need no cross-thread reduction
 //   dZ_{l-1} = dX * sigmoid(z_{l-1})   (z_{l-1}, xhat_{l-1} from a coalesced, L2-hot re-read of Y_{l-1})
-// The SAME 128-byte-swizzled [pixel row][32-channel chunk] shared-memory tile is a K-major operand in one product and
-// an MN-major operand in the other (tc_common.cuh), so G and X are staged exactly once.
-// 64-pixel tiles, two stages, 13 warps: 4 producers for G, 4 for X, 1 MMA issuer, 4 epilogue.
+// Every operand is K-major with the 128-byte swizzle (MN-major TF32 would need the 32-byte-base swizzle, i.e. a second
+// physical layout, so transposing in the producers' stores is the cheaper route: ~640 shared-memory wavefronts per tile
+// against an HBM budget of ~2800 cycles).  32-pixel tiles, three stages, 13 warps: 4 producers for G, 4 for X, 1 MMA
+// issuer, 4 epilogue.
 // =====================================================================================================================
 namespace ga {
 namespace {
 
-constexpr int kPx = 64;
-constexpr int kBChunk = kPx * 128;        // 8 KB: 32 channels x 64 pixel rows
-constexpr int kBTile = 4 * kBChunk;       // 32 KB
+constexpr int kPx = 32;
+constexpr int kBStages = 3;
+constexpr int kGkChunk = kPx * 128;       // 4 KB: [32 px rows][32 channels]
+constexpr int kGkTile = 4 * kGkChunk;     // 16 KB
+constexpr int kTTile = 128 * 128;         // 16 KB: [128 channel rows][32 px]
 constexpr int kBwdThreads = 13 * 32;
-constexpr uint32_t kBwdTmemCols = 256;    // [0,128): dW accumulator; 128 + 64 s: dX^T accumulator of stage s
+constexpr uint32_t kBwdTmemCols = 256;    // [0,128): dW accumulator; 128 + 32 s: dX^T accumulator of stage s
 
 struct TcBwdParams {
     const float *dZ, *Y; int ldg;                      // layer l: [M][ldg], 128 output channels from the pointer
@@ -278,13 +281,17 @@ struct TcBwdParams {
 };
 
 struct alignas(1024) TcBwdSmem {
-    unsigned char w[4 * kBM * 128];                    // 64 KB, rows = out channel
-    unsigned char g[2][kBTile];
-    unsigned char x[2][kBTile];
+    unsigned char wt[4 * 128 * 128];                   // 64 KB: W^T, rows = input channel, K = output channel
+    unsigned char gk[kBStages][kGkTile];               // G   rows = pixel,          K = output channel   (dgrad B operand)
+    unsigned char gt[kBStages][kTTile];                // G^T rows = output channel, K = pixel            (wgrad A operand)
+    unsigned char xt[kBStages][kTTile];                // X^T rows = input channel,  K = pixel            (wgrad B operand)
     float ga[128], m1[128], m2[128], mu[128], rstd[128], pa[128], pb[128], pmu[128], prstd[128];
-    uint64_t full[2], empty[2], mma_done[2], tmem_empty[2];
+    uint64_t full[kBStages], empty[kBStages], mma_done[kBStages], tmem_empty[kBStages];
     uint32_t tmem_base;
 };
+
+// element (row = channel ch, col = pixel px) of a transposed [128][32] K-major tile
+__device__ __forceinline__ uint32_t tr_offset(int ch, int px) { return (uint32_t)ch * 128u + (uint32_t)((((px >> 2) ^ (ch & 7)) << 4) + (px & 3) * 4); }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 tc_bwd_kernel(const TcBwdParams p)
@@ -295,17 +302,23 @@ tc_bwd_kernel(const TcBwdParams p)
     const int num_tiles = (p.M + kPx - 1) / kPx;
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kBStages; ++s) {
             mbar_init(&sm.full[s], 256); mbar_init(&sm.empty[s], 128);
             mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 128);
         }
         fence_barrier_init();
     }
     if (warp == 8) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
+    // W^T -> shared (K-major over the OUTPUT channel): element (in, out) <- W[out][in]
     for (int i = tid; i < 128 * 32; i += kBwdThreads) {
-        const int n = i >> 5, q = i & 31;
-        const float4 v = *reinterpret_cast<const float4 *>(p.W + (size_t)n * p.ldw + q * 4);
-        *reinterpret_cast<float4 *>(sm.w + (q >> 3) * (kBM * 128) + sw128_offset(n, q & 7)) = to_tf32(v);
+        const int o = i >> 5, q = i & 31;                // W row o, input channels 4q..4q+3
+        const float4 v = to_tf32(*reinterpret_cast<const float4 *>(p.W + (size_t)o * p.ldw + q * 4));
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int in = q * 4 + t;
+            *reinterpret_cast<float *>(sm.wt + (o >> 5) * (128 * 128) + in * 128 + ((((o & 31) >> 2) ^ (in & 7)) << 4) + (o & 3) * 4) = e[t];
+        }
     }
     for (int i = tid; i < 128; i += kBwdThreads) {
         sm.ga[i] = p.ga ? p.ga[i] : 1.f; sm.m1[i] = p.ga ? p.m1[i] : 0.f; sm.m2[i] = p.ga ? p.m2[i] : 0.f;
@@ -319,89 +332,89 @@ tc_bwd_kernel(const TcBwdParams p)
     const uint32_t tmem_base = sm.tmem_base;
 
     if (warp < 8) {
-        // ================================ producers: warps 0-3 build G, warps 4-7 build X ================================
+        // ================================ producers: warps 0-3 build G (two layouts), warps 4-7 build X^T ================
         const bool isG = warp < 4;
-        const int pw = warp & 3, rl = lane >> 3, u = lane & 7;
-        int it = 0;
+        const int pw = warp & 3, r8 = lane & 7, qd = lane >> 3;
+        int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int s = it & 1, n = it >> 1;
             mbar_wait(&sm.empty[s], (n & 1) ^ 1);
-            unsigned char *dst = isG ? sm.g[s] : sm.x[s];
             const int m0 = tile * kPx;
+            // the tile is 4 pixel groups (8 px) x 8 channel groups (16 ch); this warp owns 8 of the 32 blocks, 4 at a time
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int k = c * 32 + u * 4;
-                if (isG) {
-                    float4 dz[4], yy[4];
+            for (int half = 0; half < 2; ++half) {
+                float4 va[4], vb[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int m = m0 + j * 16 + pw * 4 + rl;
-                        const bool ok = m < p.M;
-                        dz[j] = ok ? *reinterpret_cast<const float4 *>(p.dZ + (size_t)m * p.ldg + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        yy[j] = (ok && p.ga) ? *reinterpret_cast<const float4 *>(p.Y + (size_t)m * p.ldg + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int e = 0; e < 4; ++e) {
+                    const int blk = pw * 8 + half * 4 + e;
+                    const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
+                    const int m = m0 + px;
+                    const bool ok = m < p.M;
+                    if (isG) {
+                        va[e] = ok ? *reinterpret_cast<const float4 *>(p.dZ + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        vb[e] = (ok && p.ga) ? *reinterpret_cast<const float4 *>(p.Y + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {
+                        va[e] = ok ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    const float4 ga = *reinterpret_cast<const float4 *>(&sm.ga[k]), m1 = *reinterpret_cast<const float4 *>(&sm.m1[k]),
-                                 m2 = *reinterpret_cast<const float4 *>(&sm.m2[k]), mu = *reinterpret_cast<const float4 *>(&sm.mu[k]),
-                                 rs = *reinterpret_cast<const float4 *>(&sm.rstd[k]);
+                }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int r = j * 16 + pw * 4 + rl;
-                        float4 gq;
-                        gq.x = ga.x * (dz[j].x - m1.x - (yy[j].x - mu.x) * rs.x * m2.x);
-                        gq.y = ga.y * (dz[j].y - m1.y - (yy[j].y - mu.y) * rs.y * m2.y);
-                        gq.z = ga.z * (dz[j].z - m1.z - (yy[j].z - mu.z) * rs.z * m2.z);
-                        gq.w = ga.w * (dz[j].w - m1.w - (yy[j].w - mu.w) * rs.w * m2.w);
-                        if (m0 + r >= p.M) gq = make_float4(0.f, 0.f, 0.f, 0.f);
-                        *reinterpret_cast<float4 *>(dst + c * kBChunk + sw128_offset(r, u)) = to_tf32(gq);
+                for (int e = 0; e < 4; ++e) {
+                    const int blk = pw * 8 + half * 4 + e;
+                    const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
+                    const bool ok = (m0 + px) < p.M;
+                    float4 o;
+                    if (isG) {
+                        const float4 ga = *reinterpret_cast<const float4 *>(&sm.ga[ch]), m1 = *reinterpret_cast<const float4 *>(&sm.m1[ch]),
+                                     m2 = *reinterpret_cast<const float4 *>(&sm.m2[ch]), mu = *reinterpret_cast<const float4 *>(&sm.mu[ch]),
+                                     rs = *reinterpret_cast<const float4 *>(&sm.rstd[ch]);
+                        o.x = ga.x * (va[e].x - m1.x - (vb[e].x - mu.x) * rs.x * m2.x);
+                        o.y = ga.y * (va[e].y - m1.y - (vb[e].y - mu.y) * rs.y * m2.y);
+                        o.z = ga.z * (va[e].z - m1.z - (vb[e].z - mu.z) * rs.z * m2.z);
+                        o.w = ga.w * (va[e].w - m1.w - (vb[e].w - mu.w) * rs.w * m2.w);
+                    } else {
+                        const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
+                        o.x = softplus_f(fmaf(va[e].x, av.x, bv.x)); o.y = softplus_f(fmaf(va[e].y, av.y, bv.y));
+                        o.z = softplus_f(fmaf(va[e].z, av.z, bv.z)); o.w = softplus_f(fmaf(va[e].w, av.w, bv.w));
                     }
-                } else {
-                    float4 yy[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int m = m0 + j * 16 + pw * 4 + rl;
-                        yy[j] = (m < p.M) ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[k]), bv = *reinterpret_cast<const float4 *>(&sm.pb[k]);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int r = j * 16 + pw * 4 + rl;
-                        float4 x;
-                        x.x = softplus_f(fmaf(yy[j].x, av.x, bv.x)); x.y = softplus_f(fmaf(yy[j].y, av.y, bv.y));
-                        x.z = softplus_f(fmaf(yy[j].z, av.z, bv.z)); x.w = softplus_f(fmaf(yy[j].w, av.w, bv.w));
-                        if (m0 + r >= p.M) x = make_float4(0.f, 0.f, 0.f, 0.f);
-                        *reinterpret_cast<float4 *>(dst + c * kBChunk + sw128_offset(r, u)) = to_tf32(x);
-                    }
+                    if (!ok) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    o = to_tf32(o);
+                    if (isG) *reinterpret_cast<float4 *>(sm.gk[s] + (ch >> 5) * kGkChunk + sw128_offset(px, (ch & 31) >> 2)) = o;
+                    unsigned char *tt = isG ? sm.gt[s] : sm.xt[s];
+                    *reinterpret_cast<float *>(tt + tr_offset(ch + 0, px)) = o.x;
+                    *reinterpret_cast<float *>(tt + tr_offset(ch + 1, px)) = o.y;
+                    *reinterpret_cast<float *>(tt + tr_offset(ch + 2, px)) = o.z;
+                    *reinterpret_cast<float *>(tt + tr_offset(ch + 3, px)) = o.w;
                 }
             }
             fence_proxy_async_smem();
             mbar_arrive(&sm.full[s]);
+            if (++s == kBStages) { s = 0; ++n; }
         }
     } else if (warp == 8) {
         // ================================ MMA issuer ================================
-        constexpr uint32_t idesc_dgrad = make_idesc_tf32(128, kPx, /*A MN-major*/ true, /*B K-major*/ false);
-        constexpr uint32_t idesc_wgrad = make_idesc_tf32(128, 128, true, true);
-        const uint32_t w_addr = smem_u32(sm.w);
-        int it = 0;
+        constexpr uint32_t idesc_dgrad = make_idesc_tf32(128, kPx, false, false);
+        constexpr uint32_t idesc_wgrad = make_idesc_tf32(128, 128, false, false);
+        const uint32_t wt_addr = smem_u32(sm.wt);
+        int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int s = it & 1, n = it >> 1;
             mbar_wait(&sm.full[s], n & 1);
             mbar_wait(&sm.tmem_empty[s], (n & 1) ^ 1);
             tc_fence_after_sync();
             if (lane == 0) {
-                const uint32_t g_addr = smem_u32(sm.g[s]), x_addr = smem_u32(sm.x[s]);
-                // dX^T[in, px] = sum_out W[out, in] G[px, out]: 16 steps of 8 output channels
+                const uint32_t gk_addr = smem_u32(sm.gk[s]), gt_addr = smem_u32(sm.gt[s]), xt_addr = smem_u32(sm.xt[s]);
+                // dX^T[in, px] = sum_out W^T[in, out] G[px, out]: 16 steps of 8 output channels
 #pragma unroll 1
                 for (int k = 0; k < 16; ++k)
-                    mma_tf32(tmem_base + 128 + (uint32_t)s * kPx, make_smem_desc(w_addr + k * 1024, kBM * 128, 1024),
-                             make_smem_desc(g_addr + (k >> 2) * kBChunk + (k & 3) * 32, 16, 1024), idesc_dgrad, k > 0);
-                // dW[out, in] += sum_px G[px, out] X[px, in]: 8 steps of 8 pixels
+                    mma_tf32(tmem_base + 128 + (uint32_t)s * kPx, make_smem_desc(wt_addr + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024),
+                             make_smem_desc(gk_addr + (k >> 2) * kGkChunk + (k & 3) * 32, 16, 1024), idesc_dgrad, k > 0);
+                // dW[out, in] += sum_px G^T[out, px] X^T[in, px]: 4 steps of 8 pixels
 #pragma unroll 1
                 for (int j = 0; j < kPx / 8; ++j)
-                    mma_tf32(tmem_base, make_smem_desc(g_addr + j * 1024, kBChunk, 1024), make_smem_desc(x_addr + j * 1024, kBChunk, 1024),
-                             idesc_wgrad, (it > 0) || (j > 0));
+                    mma_tf32(tmem_base, make_smem_desc(gt_addr + j * 32, 16, 1024), make_smem_desc(xt_addr + j * 32, 16, 1024), idesc_wgrad,
+                             (it > 0) || (j > 0));
                 mma_commit(&sm.mma_done[s]);
             }
             __syncwarp();
+            if (++s == kBStages) { s = 0; ++n; }
         }
     } else {
         // ================================ epilogue: one input channel per thread ================================
@@ -411,59 +424,52 @@ tc_bwd_kernel(const TcBwdParams p)
         const float ca = sm.pa[c], cb = sm.pb[c], cmu = sm.pmu[c], crs = sm.prstd[c];
         const bool final_mode = (p.mode == 0 || p.mode == 3);
         double d1 = 0.0, d2 = 0.0;
-        int it = 0;
+        int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int s = it & 1, n = it >> 1;
             const int m0 = tile * kPx;
             mbar_wait(&sm.mma_done[s], n & 1);
             tc_fence_after_sync();
-            float *stg = reinterpret_cast<float *>(sm.g[s]);       // both products have consumed G[s]: reuse as [px][128] staging
-            float t1 = 0.f, t2 = 0.f;
-#pragma unroll 1
-            for (int hh = 0; hh < 2; ++hh) {
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx + hh * 32, v);
-                float yv[32], ev[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int m = m0 + hh * 32 + j;
-                    yv[j] = (final_mode && m < p.M) ? p.Yprev[(size_t)m * p.ldp + c] : 0.f;
-                    ev[j] = (p.mode >= 2 && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float dx = v[j] + ev[j];
-                    if (final_mode) {
-                        const float z = fmaf(yv[j], ca, cb);
-                        dx *= sigmoid_f(z);
-                        if (m0 + hh * 32 + j < p.M) { t1 += dx; t2 = fmaf(dx, (yv[j] - cmu) * crs, t2); }
-                    }
-                    stg[(hh * 32 + j) * 128 + c] = dx;
-                }
-            }
-            d1 += (double)t1; d2 += (double)t2;
+            float *stg = reinterpret_cast<float *>(sm.gk[s]);      // both products have consumed this stage: [32 px][128] staging
+            float v[32], yv[32], ev[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx, v);
             tc_fence_before_sync();
             mbar_arrive(&sm.tmem_empty[s]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int m = m0 + j;
+                yv[j] = (final_mode && m < p.M) ? p.Yprev[(size_t)m * p.ldp + c] : 0.f;
+                ev[j] = (p.mode >= 2 && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
+            }
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float dx = v[j] + ev[j];
+                if (final_mode) {
+                    const float z = fmaf(yv[j], ca, cb);
+                    dx *= sigmoid_f(z);
+                    if (m0 + j < p.M) { t1 += dx; t2 = fmaf(dx, (yv[j] - cmu) * crs, t2); }
+                }
+                stg[j * 128 + c] = dx;
+            }
+            d1 += (double)t1; d2 += (double)t2;
             named_bar_sync(1, 128);
-            for (int r = we * 16; r < we * 16 + 16; ++r) {
+            for (int r = we * 8; r < we * 8 + 8; ++r) {
                 const int m = m0 + r;
                 if (m >= p.M) break;
                 *reinterpret_cast<float4 *>(p.dZprev + (size_t)m * p.ldo + lane * 4) = *reinterpret_cast<const float4 *>(stg + r * 128 + lane * 4);
             }
             mbar_arrive(&sm.empty[s]);
+            if (++s == kBStages) { s = 0; ++n; }
         }
         if (final_mode && p.s1) { atomicAdd(&p.s1[c], d1); atomicAdd(&p.s2[c], d2); }
         // flush the weight-gradient accumulator: lane == output channel; every MMA was covered by the last mma_done wait
         tc_fence_after_sync();
-        {
-            const int o = c;
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
+        for (int cc = 0; cc < 4; ++cc) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) atomicAdd(p.dW + (size_t)o * p.lddw + cc * 32 + j, v[j]);
-            }
+            for (int j = 0; j < 32; ++j) atomicAdd(p.dW + (size_t)c * p.lddw + cc * 32 + j, v[j]);
         }
     }
     tc_fence_before_sync();
