@@ -324,14 +324,14 @@ def main():
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         torch.cuda.synchronize()
+        warm, _ = cpu_reference_step_factory(1)            # small config: warms torch's CPU kernels / thread pool only
+        warm(0)
         step, dims = cpu_reference_step_factory(args.config)
+        t0 = time.perf_counter()
         step(0)
-        t0 = time.perf_counter(); n = 0
-        while n < 2 or (time.perf_counter() - t0 < 12.0 and n < 8):
-            step(1 + n); n += 1
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": n / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                        "sample": f"{n} full-size single-frame train steps of the oracle port (torch CPU all cores + C/OpenMP rasterizer), {dt:.1f}s"}
+        cpu_baseline = {"value": 1.0 / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"1 full-size single-frame train step of the oracle port (torch CPU all cores + C/OpenMP rasterizer, fwd+bwd+Adam), {dt:.1f}s"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
