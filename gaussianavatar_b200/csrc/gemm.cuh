@@ -17,6 +17,9 @@ constexpr int kGemmThreads = 256;
 
 __device__ __forceinline__ float softplus_f(float z) { return z > 20.f ? z : log1pf(expf(z)); }
 __device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
+// fast forms for the TF32 tensor-core path (inputs are rounded to 10 mantissa bits right after): 2 MUFU ops each
+__device__ __forceinline__ float softplus_fast(float z) { return fmaxf(z, 0.f) + __logf(1.f + __expf(-fabsf(z))); }
+__device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Fragment = what one thread holds of a (rows x 16) or (16 x cols) operand tile between global fetch and smem store.

@@ -2,11 +2,11 @@
 //
 // One persistent, warp-specialised CTA per SM computes  Y[M,128] (+)= act(bn(X))[M,K] * W[128,K]^T + bias  for its share
 // of 128-pixel tiles:
-//   warps 0-3  producers : coalesced LDG of the raw (pre-BatchNorm) input tile, BatchNorm + Softplus applied in
+//   warps 0-7  producers : coalesced LDG of the raw (pre-BatchNorm) input tile, BatchNorm + Softplus applied in
 //                          registers, STS into the 128-byte-swizzled K-major UMMA layout, fence.proxy.async, mbarrier
-//   warp  4    MMA issuer: one elected lane issues K/8 tcgen05.mma (M=128, N=128, K=8) per tile into one of two TMEM
+//   warp  8    MMA issuer: one elected lane issues K/8 tcgen05.mma (M=128, N=128, K=8) per tile into one of two TMEM
 //                          accumulators, tcgen05.commit -> mbarrier
-//   warps 5-8  epilogue  : tcgen05.ld the accumulator (lane = pixel row), + bias, stage the tile in the just-consumed
+//   warps 9-12 epilogue  : tcgen05.ld the accumulator (lane = pixel row), + bias, stage the tile in the just-consumed
 //                          input buffer (XOR-swizzled, conflict-free both ways), coalesced global stores, per-channel
 //                          sum / sum-of-squares for the layer's BatchNorm (fp32 per tile, double across tiles)
 // Two input stages + two accumulators overlap load/transform, MMA and store.  The layer is HBM-bound (64 KB in + 64 KB
@@ -26,7 +26,7 @@ constexpr int kBM = 128, kBN = 128;
 constexpr int kChunkBytes = kBM * 128;          // one 32-channel chunk of a 128-row tile: 16 KB
 constexpr int kMaxChunks = 4;                    // K <= 128
 constexpr int kStageBytes = kMaxChunks * kChunkBytes;   // 64 KB
-constexpr int kTcThreads = 9 * 32;
+constexpr int kTcThreads = 13 * 32;     // 8 producer warps, 1 MMA warp, 4 epilogue warps
 constexpr uint32_t kTmemCols = 256;
 
 struct TcFwdParams {
@@ -56,17 +56,16 @@ tc_fwd_kernel(const TcFwdParams p)
     // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand (1 KB of slack is requested)
     TcFwdSmem &sm = *reinterpret_cast<TcFwdSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int chunks = (p.K + 31) / 32;
     const int num_tiles = (p.M + kBM - 1) / kBM;
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm.full[s], 128); mbar_init(&sm.empty[s], 128);
+            mbar_init(&sm.full[s], 256); mbar_init(&sm.empty[s], 128);
             mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 128);
         }
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(&sm.tmem_base, kTmemCols);
+    if (warp == 8) tmem_alloc(&sm.tmem_base, kTmemCols);
     // weights -> shared, K-major, 128-byte swizzle
     for (int i = tid; i < kBN * (p.K / 4); i += kTcThreads) {
         const int n = i / (p.K / 4), q = i % (p.K / 4);
@@ -83,45 +82,45 @@ tc_fwd_kernel(const TcFwdParams p)
     tc_fence_after_sync();
     const uint32_t tmem_base = sm.tmem_base;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ================================ producers ================================
+        // warp w owns channel chunk c = w & 3 (its BatchNorm coefficients live in registers) and row groups 2i + (w >> 2);
+        // one warp instruction = 4 rows x 128 B.  All 16 loads of a tile are in flight before the stage is even free.
         const int rl = lane >> 3, u = lane & 7;
+        const int c = warp & 3, rg0 = warp >> 2;
+        const int k = c * 32 + u * 4;
+        const bool kin = k < p.K;
+        float4 av = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kin) { av = *reinterpret_cast<const float4 *>(&sm.sa[k]); bv = *reinterpret_cast<const float4 *>(&sm.sb[k]); }
+        const bool act = p.a != nullptr;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1, n = it >> 1;
-            mbar_wait(&sm.empty[s], (n & 1) ^ 1);
-            unsigned char *dst = sm.a[s];
             const int m0 = tile * kBM;
-            for (int c = 0; c < chunks; ++c) {
-                const int k = c * 32 + u * 4;
-                const bool kin = k < p.K;
-                float4 av = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (kin) { av = *reinterpret_cast<const float4 *>(&sm.sa[k]); bv = *reinterpret_cast<const float4 *>(&sm.sb[k]); }
+            float4 v[16];
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float4 v[4];
+            for (int i = 0; i < 16; ++i) {
+                const int m = m0 + (2 * i + rg0) * 4 + rl;
+                v[i] = (kin && m < p.M) ? *reinterpret_cast<const float4 *>(p.X + (size_t)m * p.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            mbar_wait(&sm.empty[s], (n & 1) ^ 1);
+            unsigned char *dst = sm.a[s] + c * kChunkBytes;
+            if (c * 32 < p.K) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {       // 4 loads in flight per thread, 8 per chunk
-                        const int r = (half * 4 + j) * 16 + warp * 4 + rl;
-                        const int m = m0 + r;
-                        v[j] = (kin && m < p.M) ? *reinterpret_cast<const float4 *>(p.X + (size_t)m * p.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 16; ++i) {
+                    const int r = (2 * i + rg0) * 4 + rl;
+                    float4 x = v[i];
+                    if (act) {
+                        x.x = softplus_fast(fmaf(x.x, av.x, bv.x)); x.y = softplus_fast(fmaf(x.y, av.y, bv.y));
+                        x.z = softplus_fast(fmaf(x.z, av.z, bv.z)); x.w = softplus_fast(fmaf(x.w, av.w, bv.w));
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int r = (half * 4 + j) * 16 + warp * 4 + rl;
-                        float4 x = v[j];
-                        if (p.a) {
-                            x.x = softplus_f(fmaf(x.x, av.x, bv.x)); x.y = softplus_f(fmaf(x.y, av.y, bv.y));
-                            x.z = softplus_f(fmaf(x.z, av.z, bv.z)); x.w = softplus_f(fmaf(x.w, av.w, bv.w));
-                        }
-                        *reinterpret_cast<float4 *>(dst + c * kChunkBytes + sw128_offset(r, u)) = to_tf32(x);
-                    }
+                    *reinterpret_cast<float4 *>(dst + sw128_offset(r, u)) = to_tf32(x);
                 }
             }
             fence_proxy_async_smem();
             mbar_arrive(&sm.full[s]);
         }
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ================================ MMA issuer ================================
         constexpr uint32_t idesc = make_idesc_tf32(kBM, kBN, false, false);
         const uint32_t w_addr = smem_u32(sm.w);
@@ -147,7 +146,7 @@ tc_fwd_kernel(const TcFwdParams p)
         // ================================ epilogue ================================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;               // tile row == TMEM lane
-        const int et = (warp - 5) * 32 + lane;       // 0..127: channel owned for the statistics
+        const int et = (warp - 9) * 32 + lane;       // 0..127: channel owned for the statistics
         double dsum = 0.0, dsq = 0.0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -172,7 +171,7 @@ tc_fwd_kernel(const TcFwdParams p)
             mbar_arrive(&sm.tmem_empty[s]);          // accumulator drained
             named_bar_sync(1, 128);
             // coalesced row stores (each warp: 32 rows, one 512-byte row per instruction)
-            const int wr = warp - 5;
+            const int wr = warp - 9;
             for (int r = wr * 32; r < wr * 32 + 32; ++r) {
                 const int m = m0 + r;
                 if (m >= p.M) break;
@@ -202,7 +201,7 @@ tc_fwd_kernel(const TcFwdParams p)
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace
@@ -337,53 +336,51 @@ tc_bwd_kernel(const TcBwdParams p)
         const int pw = warp & 3, r8 = lane & 7, qd = lane >> 3;
         int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            mbar_wait(&sm.empty[s], (n & 1) ^ 1);
             const int m0 = tile * kPx;
-            // the tile is 4 pixel groups (8 px) x 8 channel groups (16 ch); this warp owns 8 of the 32 blocks, 4 at a time
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                float4 va[4], vb[4];
+            // the tile is 4 pixel groups (8 px) x 8 channel groups (16 ch); this warp owns 8 of the 32 blocks.
+            // Every load of the tile is issued before the stage wait (up to 16 x 16 B per thread in flight).
+            float4 va[8], vb[8];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int blk = pw * 8 + half * 4 + e;
-                    const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
-                    const int m = m0 + px;
-                    const bool ok = m < p.M;
-                    if (isG) {
-                        va[e] = ok ? *reinterpret_cast<const float4 *>(p.dZ + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        vb[e] = (ok && p.ga) ? *reinterpret_cast<const float4 *>(p.Y + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    } else {
-                        va[e] = ok ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+            for (int e = 0; e < 8; ++e) {
+                const int blk = pw * 8 + e;
+                const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
+                const int m = m0 + px;
+                const bool ok = m < p.M;
+                if (isG) {
+                    va[e] = ok ? *reinterpret_cast<const float4 *>(p.dZ + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    vb[e] = (ok && p.ga) ? *reinterpret_cast<const float4 *>(p.Y + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                } else {
+                    va[e] = ok ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+            }
+            mbar_wait(&sm.empty[s], (n & 1) ^ 1);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int blk = pw * 8 + half * 4 + e;
-                    const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
-                    const bool ok = (m0 + px) < p.M;
-                    float4 o;
-                    if (isG) {
-                        const float4 ga = *reinterpret_cast<const float4 *>(&sm.ga[ch]), m1 = *reinterpret_cast<const float4 *>(&sm.m1[ch]),
-                                     m2 = *reinterpret_cast<const float4 *>(&sm.m2[ch]), mu = *reinterpret_cast<const float4 *>(&sm.mu[ch]),
-                                     rs = *reinterpret_cast<const float4 *>(&sm.rstd[ch]);
-                        o.x = ga.x * (va[e].x - m1.x - (vb[e].x - mu.x) * rs.x * m2.x);
-                        o.y = ga.y * (va[e].y - m1.y - (vb[e].y - mu.y) * rs.y * m2.y);
-                        o.z = ga.z * (va[e].z - m1.z - (vb[e].z - mu.z) * rs.z * m2.z);
-                        o.w = ga.w * (va[e].w - m1.w - (vb[e].w - mu.w) * rs.w * m2.w);
-                    } else {
-                        const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
-                        o.x = softplus_f(fmaf(va[e].x, av.x, bv.x)); o.y = softplus_f(fmaf(va[e].y, av.y, bv.y));
-                        o.z = softplus_f(fmaf(va[e].z, av.z, bv.z)); o.w = softplus_f(fmaf(va[e].w, av.w, bv.w));
-                    }
-                    if (!ok) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    o = to_tf32(o);
-                    if (isG) *reinterpret_cast<float4 *>(sm.gk[s] + (ch >> 5) * kGkChunk + sw128_offset(px, (ch & 31) >> 2)) = o;
-                    unsigned char *tt = isG ? sm.gt[s] : sm.xt[s];
-                    *reinterpret_cast<float *>(tt + tr_offset(ch + 0, px)) = o.x;
-                    *reinterpret_cast<float *>(tt + tr_offset(ch + 1, px)) = o.y;
-                    *reinterpret_cast<float *>(tt + tr_offset(ch + 2, px)) = o.z;
-                    *reinterpret_cast<float *>(tt + tr_offset(ch + 3, px)) = o.w;
+            for (int e = 0; e < 8; ++e) {
+                const int blk = pw * 8 + e;
+                const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
+                const bool ok = (m0 + px) < p.M;
+                float4 o;
+                if (isG) {
+                    const float4 ga = *reinterpret_cast<const float4 *>(&sm.ga[ch]), m1 = *reinterpret_cast<const float4 *>(&sm.m1[ch]),
+                                 m2 = *reinterpret_cast<const float4 *>(&sm.m2[ch]), mu = *reinterpret_cast<const float4 *>(&sm.mu[ch]),
+                                 rs = *reinterpret_cast<const float4 *>(&sm.rstd[ch]);
+                    o.x = ga.x * (va[e].x - m1.x - (vb[e].x - mu.x) * rs.x * m2.x);
+                    o.y = ga.y * (va[e].y - m1.y - (vb[e].y - mu.y) * rs.y * m2.y);
+                    o.z = ga.z * (va[e].z - m1.z - (vb[e].z - mu.z) * rs.z * m2.z);
+                    o.w = ga.w * (va[e].w - m1.w - (vb[e].w - mu.w) * rs.w * m2.w);
+                } else {
+                    const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
+                    o.x = softplus_fast(fmaf(va[e].x, av.x, bv.x)); o.y = softplus_fast(fmaf(va[e].y, av.y, bv.y));
+                    o.z = softplus_fast(fmaf(va[e].z, av.z, bv.z)); o.w = softplus_fast(fmaf(va[e].w, av.w, bv.w));
                 }
+                if (!ok) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                o = to_tf32(o);
+                if (isG) *reinterpret_cast<float4 *>(sm.gk[s] + (ch >> 5) * kGkChunk + sw128_offset(px, (ch & 31) >> 2)) = o;
+                unsigned char *tt = isG ? sm.gt[s] : sm.xt[s];
+                *reinterpret_cast<float *>(tt + tr_offset(ch + 0, px)) = o.x;
+                *reinterpret_cast<float *>(tt + tr_offset(ch + 1, px)) = o.y;
+                *reinterpret_cast<float *>(tt + tr_offset(ch + 2, px)) = o.z;
+                *reinterpret_cast<float *>(tt + tr_offset(ch + 3, px)) = o.w;
             }
             fence_proxy_async_smem();
             mbar_arrive(&sm.full[s]);
@@ -427,26 +424,27 @@ tc_bwd_kernel(const TcBwdParams p)
         int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int m0 = tile * kPx;
-            mbar_wait(&sm.mma_done[s], n & 1);
-            tc_fence_after_sync();
-            float *stg = reinterpret_cast<float *>(sm.gk[s]);      // both products have consumed this stage: [32 px][128] staging
             float v[32], yv[32], ev[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx, v);
-            tc_fence_before_sync();
-            mbar_arrive(&sm.tmem_empty[s]);
+            // independent of the MMA: fetch this channel's Y_{l-1} column (and the running partial sum) first
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int m = m0 + j;
                 yv[j] = (final_mode && m < p.M) ? p.Yprev[(size_t)m * p.ldp + c] : 0.f;
                 ev[j] = (p.mode >= 2 && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
             }
+            mbar_wait(&sm.mma_done[s], n & 1);
+            tc_fence_after_sync();
+            float *stg = reinterpret_cast<float *>(sm.gk[s]);      // both products have consumed this stage: [32 px][128] staging
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx, v);
+            tc_fence_before_sync();
+            mbar_arrive(&sm.tmem_empty[s]);
             float t1 = 0.f, t2 = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float dx = v[j] + ev[j];
                 if (final_mode) {
                     const float z = fmaf(yv[j], ca, cb);
-                    dx *= sigmoid_f(z);
+                    dx *= sigmoid_fast(z);
                     if (m0 + j < p.M) { t1 += dx; t2 = fmaf(dx, (yv[j] - cmu) * crs, t2); }
                 }
                 stg[j * 128 + c] = dx;
