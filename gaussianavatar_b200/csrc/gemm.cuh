@@ -19,6 +19,22 @@ __device__ __forceinline__ float softplus_f(float z) { return z > 20.f ? z : log
 __device__ __forceinline__ float sigmoid_f(float z) { return 1.f / (1.f + expf(-z)); }
 // fast forms for the TF32 tensor-core path (inputs are rounded to 10 mantissa bits right after): 2 MUFU ops each
 __device__ __forceinline__ float softplus_fast(float z) { return fmaxf(z, 0.f) + __logf(1.f + __expf(-fabsf(z))); }
+// sigmoid of z = zl / log2(e) given zl: 1 / (1 + 2^-zl) -> MUFU.EX2, FADD, MUFU.RCP
+__device__ __forceinline__ float sigmoid_log2(float zl)
+{
+    float t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-zl));
+    return __fdividef(1.f, 1.f + t);
+}
+// softplus of z = zl / log2(e) given zl (the BatchNorm coefficients are pre-multiplied by log2(e) once per kernel):
+// ln2 * (max(zl, 0) + log2(1 + 2^-|zl|)) -> FMNMX, MUFU.EX2, FADD, MUFU.LG2, FADD, FMUL
+__device__ __forceinline__ float softplus_log2(float zl)
+{
+    float t, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(zl)));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + t));
+    return 0.69314718056f * (fmaxf(zl, 0.f) + l);
+}
 __device__ __forceinline__ float sigmoid_fast(float z) { return __fdividef(1.f, 1.f + __expf(-z)); }
 
 // ---------------------------------------------------------------------------------------------------------------

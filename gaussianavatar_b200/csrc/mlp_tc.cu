@@ -53,8 +53,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 tc_fwd_kernel(const TcFwdParams p)
 {
     extern __shared__ unsigned char smem_raw[];
-    // SWIZZLE_128B operands need 1024-byte aligned tiles: align the dynamic window by hand (1 KB of slack is requested)
-    TcFwdSmem &sm = *reinterpret_cast<TcFwdSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // SWIZZLE_128B operands need 1024-byte aligned tiles: skip to the next 1 KB boundary (1 KB of slack is requested).
+    // Pointer arithmetic on the extern array keeps the shared address space visible to the compiler (LDS/STS, not LD/ST).
+    TcFwdSmem &sm = *reinterpret_cast<TcFwdSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int num_tiles = (p.M + kBM - 1) / kBM;
 
@@ -93,6 +94,10 @@ tc_fwd_kernel(const TcFwdParams p)
         float4 av = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kin) { av = *reinterpret_cast<const float4 *>(&sm.sa[k]); bv = *reinterpret_cast<const float4 *>(&sm.sb[k]); }
         const bool act = p.a != nullptr;
+        {   // work in the log2 domain: z * log2(e) comes straight out of the FMA
+            const float L2E = 1.44269504089f;
+            av.x *= L2E; av.y *= L2E; av.z *= L2E; av.w *= L2E; bv.x *= L2E; bv.y *= L2E; bv.z *= L2E; bv.w *= L2E;
+        }
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1, n = it >> 1;
@@ -111,8 +116,8 @@ tc_fwd_kernel(const TcFwdParams p)
                     const int r = (2 * i + rg0) * 4 + rl;
                     float4 x = v[i];
                     if (act) {
-                        x.x = softplus_fast(fmaf(x.x, av.x, bv.x)); x.y = softplus_fast(fmaf(x.y, av.y, bv.y));
-                        x.z = softplus_fast(fmaf(x.z, av.z, bv.z)); x.w = softplus_fast(fmaf(x.w, av.w, bv.w));
+                        x.x = softplus_log2(fmaf(x.x, av.x, bv.x)); x.y = softplus_log2(fmaf(x.y, av.y, bv.y));
+                        x.z = softplus_log2(fmaf(x.z, av.z, bv.z)); x.w = softplus_log2(fmaf(x.w, av.w, bv.w));
                     }
                     *reinterpret_cast<float4 *>(dst + sw128_offset(r, u)) = to_tf32(x);
                 }
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 tc_bwd_kernel(const TcBwdParams p)
 {
     extern __shared__ unsigned char smem_raw[];
-    TcBwdSmem &sm = *reinterpret_cast<TcBwdSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    TcBwdSmem &sm = *reinterpret_cast<TcBwdSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int num_tiles = (p.M + kPx - 1) / kPx;
 
@@ -322,7 +327,8 @@ tc_bwd_kernel(const TcBwdParams p)
     for (int i = tid; i < 128; i += kBwdThreads) {
         sm.ga[i] = p.ga ? p.ga[i] : 1.f; sm.m1[i] = p.ga ? p.m1[i] : 0.f; sm.m2[i] = p.ga ? p.m2[i] : 0.f;
         sm.mu[i] = p.ga ? p.mu[i] : 0.f; sm.rstd[i] = p.ga ? p.rstd[i] : 0.f;
-        sm.pa[i] = p.pa[i]; sm.pb[i] = p.pb[i]; sm.pmu[i] = p.pmu[i]; sm.prstd[i] = p.prstd[i];
+        // layer l-1's folded BatchNorm in the log2 domain: z * log2(e) = y * pa + pb (softplus_log2 / sigmoid_log2)
+        sm.pa[i] = p.pa[i] * 1.44269504089f; sm.pb[i] = p.pb[i] * 1.44269504089f; sm.pmu[i] = p.pmu[i]; sm.prstd[i] = p.prstd[i];
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -370,8 +376,8 @@ tc_bwd_kernel(const TcBwdParams p)
                     o.w = ga.w * (va[e].w - m1.w - (vb[e].w - mu.w) * rs.w * m2.w);
                 } else {
                     const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
-                    o.x = softplus_fast(fmaf(va[e].x, av.x, bv.x)); o.y = softplus_fast(fmaf(va[e].y, av.y, bv.y));
-                    o.z = softplus_fast(fmaf(va[e].z, av.z, bv.z)); o.w = softplus_fast(fmaf(va[e].w, av.w, bv.w));
+                    o.x = softplus_log2(fmaf(va[e].x, av.x, bv.x)); o.y = softplus_log2(fmaf(va[e].y, av.y, bv.y));
+                    o.z = softplus_log2(fmaf(va[e].z, av.z, bv.z)); o.w = softplus_log2(fmaf(va[e].w, av.w, bv.w));
                 }
                 if (!ok) o = make_float4(0.f, 0.f, 0.f, 0.f);
                 o = to_tf32(o);
@@ -443,8 +449,7 @@ tc_bwd_kernel(const TcBwdParams p)
             for (int j = 0; j < 32; ++j) {
                 float dx = v[j] + ev[j];
                 if (final_mode) {
-                    const float z = fmaf(yv[j], ca, cb);
-                    dx *= sigmoid_fast(z);
+                    dx *= sigmoid_log2(fmaf(yv[j], ca, cb));
                     if (m0 + j < p.M) { t1 += dx; t2 = fmaf(dx, (yv[j] - cmu) * crs, t2); }
                 }
                 stg[j * 128 + c] = dx;

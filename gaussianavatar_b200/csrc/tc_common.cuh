@@ -88,12 +88,9 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32])
 }
 
 // fp32 -> tf32 with round-to-nearest (the tensor core itself would truncate the low 13 mantissa bits)
-__device__ __forceinline__ float to_tf32(float x)
-{
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
+// cvt.rna.tf32.f32 == add half an ulp of the 10-bit mantissa, then drop 13 bits; the tensor core does the dropping
+// itself when it reads the operand, so one integer add per element is all that is needed.
+__device__ __forceinline__ float to_tf32(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ float4 to_tf32(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
 
 // ---- descriptors -----------------------------------------------------------------------------------------------------
