@@ -18,7 +18,7 @@
 namespace ga {
 int launch_tc_bwd(const float *dZ, const float *Y, int ldg, const float *ga, const float *m1, const float *m2, const float *mu, const float *rstd,
                   const float *Yprev, int ldp, const float *pa, const float *pb, const float *pmu, const float *prstd, const float *W, int ldw,
-                  float *dW, int lddw, float *dZprev, int ldo, int mode, double *s1, double *s2, int M, cudaStream_t st);
+                  float *dW, int lddw, float *dZprev, int ldo, int mode, double *s1, double *s2, int M, int kin, int x_raw, cudaStream_t st);
 int launch_tc_fwd(const float *X, int ldx, int K, const float *a, const float *b, const float *W, int ldw, const float *bias, float *Y,
                   int ldy, int accumulate, double *sum, double *sumsq, int M, cudaStream_t st);
 namespace {
@@ -664,7 +664,7 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         auto tc = [&](const float *dZl, const float *Yl, int ldg, int ol, const float *Yp, int ldp, int op, const float *Wl, int ldw, float *dWl,
                       float *dZp, int ldo, int mode) -> int {
             return launch_tc_bwd(dZl, Yl, ldg, cf.ga + ol, cf.m1 + ol, cf.m2 + ol, cf.mean + ol, cf.rstd + ol, Yp, ldp, cf.a + op, cf.b + op,
-                                 cf.mean + op, cf.rstd + op, Wl, ldw, dWl, ldw, dZp, ldo, mode, s1 + op, s2 + op, M, st);
+                                 cf.mean + op, cf.rstd + op, Wl, ldw, dWl, ldw, dZp, ldo, mode, s1 + op, s2 + op, M, kH, 0, st);
         };
         for (int h = 0; h < 3; ++h)      // layer 7 heads -> dZ6[:, h]
             if (int rc = tc(w.dZ7 + h * kH, w.Y7 + h * kH, 3 * kH, kBnOff[6] + h * kH, w.Y6 + h * kH, 3 * kH, kBnOff[5] + h * kH,
@@ -677,14 +677,10 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         {   // layer 5: x4 part on the tensor cores, the 72-wide feature part on the CUDA cores
             const int o5 = kBnOff[4];
             if (int rc = tc(w.dZa, w.Y[4], kH, o5, w.Y[3], kH, kBnOff[3], params + L.w[4] + kFeatLd, kK5, d_params + L.w[4] + kFeatLd, w.dZb, kH, 0)) return rc;
-            ALoadBnBwdD<128> A{w.dZa, w.Y[4], kH, bwdcoef(o5), kH, M};
-            BLoadConcatActD<128> B{w.feat, kFeatLd, kFeatLd, nullptr, 0, ChanAffine{nullptr, nullptr}, kFeatLd, M};
-            EpiAtomicAdd E{d_params + L.w[4], kK5, kH, kFeatLd};
-            if (int rc = launch_gemm<128, 128>("mlp_wgrad_l5_feat", A, B, E, kH, kFeatLd, M, kSplit, st)) return rc;
-            ALoadBnBwdK<128> A2{w.dZa, w.Y[4], kH, bwdcoef(o5), M, kH};
-            BLoadDirect<128> B2{params + L.w[4], kK5, kFeatLd, kH};
-            EpiDgradAct E2{M, kFeatLd, kFeatLd, w.d_feat, kFeatLd, false, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-            if (int rc = launch_gemm<128, 128>("mlp_dgrad_l5_feat", A2, B2, E2, M, kFeatLd, kH, 1, st)) return rc;
+            // the 72-wide [features | uv] part of conv5: raw input, gradient stored into d_feat (layer 1 adds to it later)
+            if (int rc = launch_tc_bwd(w.dZa, w.Y[4], kH, cf.ga + o5, cf.m1 + o5, cf.m2 + o5, cf.mean + o5, cf.rstd + o5, w.feat, kFeatLd, nullptr,
+                                       nullptr, nullptr, nullptr, params + L.w[4], kK5, d_params + L.w[4], kK5, w.d_feat, kFeatLd, 1, nullptr,
+                                       nullptr, M, kFeatLd, 1, st)) return rc;
             if (int rc = finalize(3, kH)) return rc;
         }
         cur = w.dZb; nxt = w.dZa;
@@ -754,6 +750,12 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
     }
     }
     // layer 1: cur = dZ1
+    if (d->flags & GA_DECODER_TENSOR_CORES) {
+        const int o1 = kBnOff[0];
+        if (int rc = launch_tc_bwd(cur, w.Y[0], kH, cf.ga + o1, cf.m1 + o1, cf.m2 + o1, cf.mean + o1, cf.rstd + o1, w.feat, kFeatLd, nullptr, nullptr,
+                                   nullptr, nullptr, params + L.w[0], kFeatLd, d_params + L.w[0], kFeatLd, w.d_feat, kFeatLd, 2, nullptr, nullptr, M,
+                                   kFeatLd, 1, st)) return rc;
+    } else
     {
         const int o1 = kBnOff[0];
         ALoadBnBwdD<128> A{cur, w.Y[0], kH, bwdcoef(o1), kH, M};

@@ -282,6 +282,8 @@ struct TcBwdParams {
     int mode;                                          // 0 final, 1 store raw dX, 2 accumulate raw dX, 3 final on (existing + dX)
     double *s1, *s2;
     int M;
+    int kin;                                           // valid input channels (128, or 72 for the [features|uv] input)
+    int x_raw;                                         // X = Yprev as is (the network input: no BatchNorm / Softplus; modes 1, 2 only)
 };
 
 struct alignas(1024) TcBwdSmem {
@@ -314,8 +316,10 @@ tc_bwd_kernel(const TcBwdParams p)
     }
     if (warp == 8) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
     // W^T -> shared (K-major over the OUTPUT channel): element (in, out) <- W[out][in]
-    for (int i = tid; i < 128 * 32; i += kBwdThreads) {
-        const int o = i >> 5, q = i & 31;                // W row o, input channels 4q..4q+3
+    const int kq = p.kin >> 2;
+    for (int i = tid; i < 128 * kq; i += kBwdThreads) {
+        const int o = i / kq, q = i % kq;                // W row o, input channels 4q..4q+3 (rows >= kin of W^T stay undefined:
+                                                         // they only feed accumulator rows / columns that are never stored)
         const float4 v = to_tf32(*reinterpret_cast<const float4 *>(p.W + (size_t)o * p.ldw + q * 4));
         const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -328,7 +332,8 @@ tc_bwd_kernel(const TcBwdParams p)
         sm.ga[i] = p.ga ? p.ga[i] : 1.f; sm.m1[i] = p.ga ? p.m1[i] : 0.f; sm.m2[i] = p.ga ? p.m2[i] : 0.f;
         sm.mu[i] = p.ga ? p.mu[i] : 0.f; sm.rstd[i] = p.ga ? p.rstd[i] : 0.f;
         // layer l-1's folded BatchNorm in the log2 domain: z * log2(e) = y * pa + pb (softplus_log2 / sigmoid_log2)
-        sm.pa[i] = p.pa[i] * 1.44269504089f; sm.pb[i] = p.pb[i] * 1.44269504089f; sm.pmu[i] = p.pmu[i]; sm.prstd[i] = p.prstd[i];
+        sm.pa[i] = p.x_raw ? 1.f : p.pa[i] * 1.44269504089f; sm.pb[i] = p.x_raw ? 0.f : p.pb[i] * 1.44269504089f;
+        sm.pmu[i] = p.x_raw ? 0.f : p.pmu[i]; sm.prstd[i] = p.x_raw ? 0.f : p.prstd[i];
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -356,7 +361,7 @@ tc_bwd_kernel(const TcBwdParams p)
                     va[e] = ok ? *reinterpret_cast<const float4 *>(p.dZ + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
                     vb[e] = (ok && p.ga) ? *reinterpret_cast<const float4 *>(p.Y + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
                 } else {
-                    va[e] = ok ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    va[e] = (ok && ch < p.kin) ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             mbar_wait(&sm.empty[s], (n & 1) ^ 1);
@@ -374,6 +379,8 @@ tc_bwd_kernel(const TcBwdParams p)
                     o.y = ga.y * (va[e].y - m1.y - (vb[e].y - mu.y) * rs.y * m2.y);
                     o.z = ga.z * (va[e].z - m1.z - (vb[e].z - mu.z) * rs.z * m2.z);
                     o.w = ga.w * (va[e].w - m1.w - (vb[e].w - mu.w) * rs.w * m2.w);
+                } else if (p.x_raw) {
+                    o = va[e];
                 } else {
                     const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
                     o.x = softplus_log2(fmaf(va[e].x, av.x, bv.x)); o.y = softplus_log2(fmaf(va[e].y, av.y, bv.y));
@@ -426,6 +433,7 @@ tc_bwd_kernel(const TcBwdParams p)
         const int we = warp - 9;                     // 0..3 for the coalesced store phase
         const float ca = sm.pa[c], cb = sm.pb[c], cmu = sm.pmu[c], crs = sm.prstd[c];
         const bool final_mode = (p.mode == 0 || p.mode == 3);
+        const bool cvalid = c < p.kin;
         double d1 = 0.0, d2 = 0.0;
         int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -435,8 +443,8 @@ tc_bwd_kernel(const TcBwdParams p)
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int m = m0 + j;
-                yv[j] = (final_mode && m < p.M) ? p.Yprev[(size_t)m * p.ldp + c] : 0.f;
-                ev[j] = (p.mode >= 2 && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
+                yv[j] = (final_mode && cvalid && m < p.M) ? p.Yprev[(size_t)m * p.ldp + c] : 0.f;
+                ev[j] = (p.mode >= 2 && cvalid && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
             }
             mbar_wait(&sm.mma_done[s], n & 1);
             tc_fence_after_sync();
@@ -459,7 +467,8 @@ tc_bwd_kernel(const TcBwdParams p)
             for (int r = we * 8; r < we * 8 + 8; ++r) {
                 const int m = m0 + r;
                 if (m >= p.M) break;
-                *reinterpret_cast<float4 *>(p.dZprev + (size_t)m * p.ldo + lane * 4) = *reinterpret_cast<const float4 *>(stg + r * 128 + lane * 4);
+                if (lane * 4 < p.kin)
+                    *reinterpret_cast<float4 *>(p.dZprev + (size_t)m * p.ldo + lane * 4) = *reinterpret_cast<const float4 *>(stg + r * 128 + lane * 4);
             }
             mbar_arrive(&sm.empty[s]);
             if (++s == kBStages) { s = 0; ++n; }
@@ -472,7 +481,8 @@ tc_bwd_kernel(const TcBwdParams p)
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(p.dW + (size_t)c * p.lddw + cc * 32 + j, v[j]);
+            for (int j = 0; j < 32; ++j)
+                if (cc * 32 + j < p.kin) atomicAdd(p.dW + (size_t)c * p.lddw + cc * 32 + j, v[j]);
         }
     }
     tc_fence_before_sync();
@@ -484,15 +494,16 @@ tc_bwd_kernel(const TcBwdParams p)
 
 int launch_tc_bwd(const float *dZ, const float *Y, int ldg, const float *ga, const float *m1, const float *m2, const float *mu, const float *rstd,
                   const float *Yprev, int ldp, const float *pa, const float *pb, const float *pmu, const float *prstd, const float *W, int ldw,
-                  float *dW, int lddw, float *dZprev, int ldo, int mode, double *s1, double *s2, int M, cudaStream_t st)
+                  float *dW, int lddw, float *dZprev, int ldo, int mode, double *s1, double *s2, int M, int kin, int x_raw, cudaStream_t st)
 {
+    GA_REQUIRE(kin % 4 == 0 && kin >= 4 && kin <= 128 && (!x_raw || mode == 1 || mode == 2), "tcgen05 backward: bad kin / mode");
     GA_REQUIRE(ldg % 4 == 0 && ldp % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0, "tcgen05 backward: leading dimensions must be multiples of 4");
     static bool attr_set = false;
     if (!attr_set) {
         GA_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcBwdSmem) + 1024));
         attr_set = true;
     }
-    TcBwdParams p{dZ, Y, ldg, ga, m1, m2, mu, rstd, Yprev, ldp, pa, pb, pmu, prstd, W, ldw, dW, lddw, dZprev, ldo, mode, s1, s2, M};
+    TcBwdParams p{dZ, Y, ldg, ga, m1, m2, mu, rstd, Yprev, ldp, pa, pb, pmu, prstd, W, ldw, dW, lddw, dZprev, ldo, mode, s1, s2, M, kin, x_raw};
     const int tiles = cdiv(M, kPx);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     {
@@ -514,5 +525,5 @@ extern "C" int ga_tc_linear_backward(int32_t M, const float *dZ, const float *Y,
     const float *bc = bwd_coef;
     return ga::launch_tc_bwd(dZ, Y, ldg, bc, bc ? bc + 128 : nullptr, bc ? bc + 256 : nullptr, bc ? bc + 384 : nullptr, bc ? bc + 512 : nullptr, Yprev,
                              ldp, prev_coef, prev_coef + 128, prev_coef + 256, prev_coef + 384, W, ldw, dW, lddw, dZprev, ldo, mode, s1, s2, M,
-                             static_cast<cudaStream_t>(stream));
+                             128, 0, static_cast<cudaStream_t>(stream));
 }
