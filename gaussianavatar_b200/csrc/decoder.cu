@@ -241,6 +241,7 @@ __global__ void bn_finalize_bwd_kernel(int C, double count, const double *__rest
 
 // Final 1x1 convs of the three heads (conv8 128->3, conv8N 128->1 + sigmoid, conv8SH 128->3 + sigmoid,
 // modules.py:566-580) fused with the last BN + Softplus: 8 lanes per pixel, 16 channels per lane and head.
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 heads_fwd_kernel(size_t M, const float *__restrict__ Y7 /*[M,384]*/, const float *__restrict__ a7, const float *__restrict__ b7,
                  const float *__restrict__ W8 /*[8,128]*/, const float *__restrict__ b8, float *__restrict__ dec /*[M,8]*/)
@@ -259,8 +260,11 @@ heads_fwd_kernel(size_t M, const float *__restrict__ Y7 /*[M,384]*/, const float
             for (int i = 0; i < 4; ++i) {
                 const int c = l * 4 + 32 * i;
                 const float4 y = *reinterpret_cast<const float4 *>(Y7 + m * 3 * kH + h * kH + c);
-                const float x[4] = {softplus_f(fmaf(y.x, sa[h * kH + c], sb[h * kH + c])), softplus_f(fmaf(y.y, sa[h * kH + c + 1], sb[h * kH + c + 1])),
-                                    softplus_f(fmaf(y.z, sa[h * kH + c + 2], sb[h * kH + c + 2])), softplus_f(fmaf(y.w, sa[h * kH + c + 3], sb[h * kH + c + 3]))};
+                const float z4[4] = {fmaf(y.x, sa[h * kH + c], sb[h * kH + c]), fmaf(y.y, sa[h * kH + c + 1], sb[h * kH + c + 1]),
+                                     fmaf(y.z, sa[h * kH + c + 2], sb[h * kH + c + 2]), fmaf(y.w, sa[h * kH + c + 3], sb[h * kH + c + 3])};
+                float x[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = FAST ? softplus_fast(z4[e]) : softplus_f(z4[e]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     if (h == 0) { p[0] = fmaf(x[e], sW[0][c + e], p[0]); p[1] = fmaf(x[e], sW[1][c + e], p[1]); p[2] = fmaf(x[e], sW[2][c + e], p[2]); }
@@ -285,7 +289,7 @@ heads_fwd_kernel(size_t M, const float *__restrict__ Y7 /*[M,384]*/, const float
 
 // Backward of one head's final conv (+ sigmoid) and of the BN+Softplus feeding it.  HEAD 0: xyz (rows 0-2),
 // 1: scale (row 3), 2: colour (rows 4-6).  Writes dZ7[:, head*128 ...], accumulates s1/s2 (double), dW8 rows, db8.
-template <int HEAD>
+template <int HEAD, bool FAST>
 __global__ void __launch_bounds__(256)
 heads_bwd_kernel(size_t M, const float *__restrict__ Y7, const float *__restrict__ a7, const float *__restrict__ b7,
                  const float *__restrict__ mu7, const float *__restrict__ rstd7, const float *__restrict__ W8,
@@ -333,11 +337,11 @@ heads_bwd_kernel(size_t M, const float *__restrict__ Y7, const float *__restrict
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float z = fmaf(y[e], sa[c + e], sb[c + e]);
-                const float x = softplus_f(z);
+                const float x = FAST ? softplus_fast(z) : softplus_f(z);
                 float dx = 0.f;
 #pragma unroll
                 for (int o = 0; o < NOUT; ++o) { dx = fmaf(dp[o], sW[o][c + e], dx); aw[o][i * 4 + e] = fmaf(dp[o], x, aw[o][i * 4 + e]); }
-                dz[e] = dx * sigmoid_f(z);
+                dz[e] = dx * (FAST ? sigmoid_fast(z) : sigmoid_f(z));
                 a1[i * 4 + e] += dz[e];
                 a2[i * 4 + e] = fmaf(dz[e], (y[e] - smu[c + e]) * srs[c + e], a2[i * 4 + e]);
             }
@@ -600,7 +604,10 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
     if (int rc = finalize(6, 3 * kH)) return rc;
     {
         ProfScope _ps("heads_fwd_kernel", st);
-        heads_fwd_kernel<<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
+        if (d->flags & GA_DECODER_TENSOR_CORES)
+            heads_fwd_kernel<true><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
+        else
+            heads_fwd_kernel<false><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
     }
     GA_CHECK_LAUNCH("heads_fwd_kernel");
     return GA_OK;
@@ -640,20 +647,32 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         const int o7 = kBnOff[6];
         {
             ProfScope _ps("heads_bwd_kernel<0>", st);
-            heads_bwd_kernel<0><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8, dec_out,
-                                                             d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+            if (d->flags & GA_DECODER_TENSOR_CORES)
+                heads_bwd_kernel<0, true><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                                                                   dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+            else
+                heads_bwd_kernel<0, false><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                                                                    dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
         }
         GA_CHECK_LAUNCH("heads_bwd_kernel<0>");
         {
             ProfScope _ps("heads_bwd_kernel<1>", st);
-            heads_bwd_kernel<1><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8, dec_out,
-                                                             d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+            if (d->flags & GA_DECODER_TENSOR_CORES)
+                heads_bwd_kernel<1, true><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                                                                   dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+            else
+                heads_bwd_kernel<1, false><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                                                                    dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
         }
         GA_CHECK_LAUNCH("heads_bwd_kernel<1>");
         {
             ProfScope _ps("heads_bwd_kernel<2>", st);
-            heads_bwd_kernel<2><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8, dec_out,
-                                                             d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+            if (d->flags & GA_DECODER_TENSOR_CORES)
+                heads_bwd_kernel<2, true><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                                                                   dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
+            else
+                heads_bwd_kernel<2, false><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                                                                    dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
         }
         GA_CHECK_LAUNCH("heads_bwd_kernel<2>");
         if (int rc = finalize(6, 3 * kH)) return rc;

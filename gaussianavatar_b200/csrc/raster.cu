@@ -358,8 +358,39 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-// K7: per pixel, back to front.  Per-Gaussian gradients are reduced warp-wide with shuffles, then across the CTA's
-// eight warps in shared memory, so each (tile, Gaussian) pair issues at most one global atomic per component.
+// Reduce 8 per-lane values across the warp with 9 shuffles (recursive halving: after the xor-16 / 8 / 4 steps a lane
+// holds ONE of the eight sums over 8 lanes, the xor-2 / 1 steps finish it).  Returns the sum of value
+// `idx = 4*bit4(lane) + 2*bit3(lane) + bit2(lane)` over all 32 lanes (replicated over the lane's 4-lane group).
+__device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane)
+{
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h4 ? v[i] : v[i + 4];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        v[i] = (h4 ? v[i + 4] : v[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h3 ? v[i] : v[i + 2];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        v[i] = (h3 ? v[i + 2] : v[i]) + recv;
+    }
+    {
+        const float send = h2 ? v[0] : v[1];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        v[0] = (h2 ? v[1] : v[0]) + recv;
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
+// K7: per pixel, back to front.  Per-Gaussian gradients are reduced warp-wide with shuffles (9 per Gaussian for the 8
+// components GaussianAvatar consumes), then across the CTA's eight warps in shared memory, so each (tile, Gaussian) pair
+// issues at most one global atomic per component.  kOpacity adds dL/dopacity (API completeness; the avatar's opacity is
+// a constant without gradient, model/avatar_model.py:80).
+template <bool kOpacity>
 __global__ void __launch_bounds__(kBlock)
 render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
                   const float *__restrict__ bg, const float2 *__restrict__ xy, const float4 *__restrict__ conic_o,
@@ -406,6 +437,7 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
     const int rounds = (int)((todo + kBlock - 1) / kBlock);
+    const int vidx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // component this lane ends up owning
 
     for (int r = 0; r < rounds; ++r) {
         __syncthreads();
@@ -438,9 +470,10 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
                 }
             }
             if (!__any_sync(0xffffffffu, active)) continue;
-            float v[9];
+            float v[8];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) v[k] = 0.f;
+            for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            float vo = 0.f;
             if (active) {
                 T = T / (1.f - alpha);
                 const float dchannel_dcolor = alpha * T;
@@ -462,13 +495,13 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
                 v[5] = -0.5f * gdx * dx * dL_dG;
                 v[6] = -0.5f * gdx * dy * dL_dG;
                 v[7] = -0.5f * gdy * dy * dL_dG;
-                v[8] = G * dL_dalpha;
+                vo = G * dL_dalpha;
             }
-#pragma unroll
-            for (int k = 0; k < 9; ++k) v[k] = warp_sum(v[k]);
-            if (lane == 0) {
-#pragma unroll
-                for (int k = 0; k < 9; ++k) atomicAdd(&s_acc[k][j], v[k]);
+            const float red = warp_reduce8(v, lane);
+            if ((lane & 3) == 0) atomicAdd(&s_acc[vidx][j], red);
+            if (kOpacity) {
+                vo = warp_sum(vo);
+                if (lane == 0) atomicAdd(&s_acc[8][j], vo);
             }
         }
         __syncthreads();
@@ -485,7 +518,7 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
             if (a[5] != 0.f) atomicAdd(&d_conic_op[g].x, a[5]);
             if (a[6] != 0.f) atomicAdd(&d_conic_op[g].y, a[6]);
             if (a[7] != 0.f) atomicAdd(&d_conic_op[g].z, a[7]);
-            if (a[8] != 0.f) atomicAdd(&d_conic_op[g].w, a[8]);
+            if (kOpacity && a[8] != 0.f) atomicAdd(&d_conic_op[g].w, a[8]);
         }
     }
 }
@@ -747,7 +780,12 @@ extern "C" int ga_raster_backward(const GaRasterSettings *s, const float *means3
         BinViews b = carve_bin(const_cast<void *>(binning), R, s->H, s->W);
         {
             ProfScope _ps("render_bwd_kernel", stream);
-            render_bwd_kernel<<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, bg, g.xy,
+            if (d_opacities)
+                render_bwd_kernel<true><<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, bg, g.xy,
+                                                                              g.conic_o, colors, iv.final_T, iv.n_contrib,
+                                                                              dL_dout, d_mean2D, d_conic_op, d_colors);
+            else
+                render_bwd_kernel<false><<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, bg, g.xy,
                                                                               g.conic_o, colors, iv.final_T, iv.n_contrib,
                                                                               dL_dout, d_mean2D, d_conic_op, d_colors);
         }
