@@ -26,6 +26,14 @@ def adjust_loss_weights(init_weight, current_epoch, mode="decay", start=400, eve
     return init_weight * (factor ** ((current_epoch - start) // every))
 
 
+def allreduce_gradients(grads, group=None):
+    """SUM all-reduce of a list of gradient tensors (asynchronously issued, then waited).  The caller divides by the world
+    size (FusedAdam.grad_scale).  Works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)."""
+    works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group, async_op=True) for g in grads if g is not None]
+    for w in works:
+        w.wait()
+
+
 class Stage1Trainer:
     def __init__(self, model, fused_adam: bool = True, process_group=None):
         self.model = model
@@ -56,10 +64,7 @@ class Stage1Trainer:
         if self.world == 1:
             return
         m = self.model
-        grads = [m.net.flat.grad, m.geo_feature.grad]
-        works = [dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True) for g in grads if g is not None]
-        for w in works:
-            w.wait()
+        allreduce_gradients([m.net.flat.grad, m.geo_feature.grad], self.group)
 
     def step(self, batch, iteration: int, epoch: int = 0):
         m = self.model
