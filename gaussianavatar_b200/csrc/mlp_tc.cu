@@ -268,7 +268,8 @@ constexpr int kBStages = 3;
 constexpr int kGkChunk = kPx * 128;       // 4 KB: [32 px rows][32 channels]
 constexpr int kGkTile = 4 * kGkChunk;     // 16 KB
 constexpr int kTTile = 128 * 128;         // 16 KB: [128 channel rows][32 px]
-constexpr int kBwdThreads = 13 * 32;
+constexpr int kBwdThreads = 21 * 32;      // 8 G-producer warps, 4 X-producer warps, 1 MMA warp, 8 epilogue warps
+constexpr int kBwdMmaWarp = 12, kBwdEpiWarp0 = 13;
 constexpr uint32_t kBwdTmemCols = 256;    // [0,128): dW accumulator; 128 + 32 s: dX^T accumulator of stage s
 
 struct TcBwdParams {
@@ -291,13 +292,11 @@ struct alignas(1024) TcBwdSmem {
     unsigned char gk[kBStages][kGkTile];               // G   rows = pixel,          K = output channel   (dgrad B operand)
     unsigned char gt[kBStages][kTTile];                // G^T rows = output channel, K = pixel            (wgrad A operand)
     unsigned char xt[kBStages][kTTile];                // X^T rows = input channel,  K = pixel            (wgrad B operand)
-    float ga[128], m1[128], m2[128], mu[128], rstd[128], pa[128], pb[128], pmu[128], prstd[128];
+    float gA[128], gB[128], gC[128];                   // dY = gA dZ + gB Y + gC  (BatchNorm backward folded to two FMAs)
+    float pa[128], pb[128], pbeta[128], pinvg[128];    // layer l-1: z log2e = y pa + pb ; xhat = (z - pbeta) * pinvg
     uint64_t full[kBStages], empty[kBStages], mma_done[kBStages], tmem_empty[kBStages];
     uint32_t tmem_base;
 };
-
-// element (row = channel ch, col = pixel px) of a transposed [128][32] K-major tile
-__device__ __forceinline__ uint32_t tr_offset(int ch, int px) { return (uint32_t)ch * 128u + (uint32_t)((((px >> 2) ^ (ch & 7)) << 4) + (px & 3) * 4); }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 tc_bwd_kernel(const TcBwdParams p)
@@ -309,12 +308,12 @@ tc_bwd_kernel(const TcBwdParams p)
 
     if (tid == 0) {
         for (int s = 0; s < kBStages; ++s) {
-            mbar_init(&sm.full[s], 256); mbar_init(&sm.empty[s], 128);
-            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 128);
+            mbar_init(&sm.full[s], 12 * 32); mbar_init(&sm.empty[s], 8 * 32);
+            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 8 * 32);
         }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
+    if (warp == kBwdMmaWarp) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
     // W^T -> shared (K-major over the OUTPUT channel): element (in, out) <- W[out][in]
     const int kq = p.kin >> 2;
     for (int i = tid; i < 128 * kq; i += kBwdThreads) {
@@ -329,11 +328,18 @@ tc_bwd_kernel(const TcBwdParams p)
         }
     }
     for (int i = tid; i < 128; i += kBwdThreads) {
-        sm.ga[i] = p.ga ? p.ga[i] : 1.f; sm.m1[i] = p.ga ? p.m1[i] : 0.f; sm.m2[i] = p.ga ? p.m2[i] : 0.f;
-        sm.mu[i] = p.ga ? p.mu[i] : 0.f; sm.rstd[i] = p.ga ? p.rstd[i] : 0.f;
-        // layer l-1's folded BatchNorm in the log2 domain: z * log2(e) = y * pa + pb (softplus_log2 / sigmoid_log2)
-        sm.pa[i] = p.x_raw ? 1.f : p.pa[i] * 1.44269504089f; sm.pb[i] = p.x_raw ? 0.f : p.pb[i] * 1.44269504089f;
-        sm.pmu[i] = p.x_raw ? 0.f : p.pmu[i]; sm.prstd[i] = p.x_raw ? 0.f : p.prstd[i];
+        if (p.ga) {   // ga (dZ - m1 - (Y - mu) rstd m2)
+            const float ga = p.ga[i], k = p.rstd[i] * p.m2[i];
+            sm.gA[i] = ga; sm.gB[i] = -ga * k; sm.gC[i] = ga * (k * p.mu[i] - p.m1[i]);
+        } else { sm.gA[i] = 1.f; sm.gB[i] = 0.f; sm.gC[i] = 0.f; }
+        if (p.x_raw) { sm.pa[i] = 1.f; sm.pb[i] = 0.f; sm.pbeta[i] = 0.f; sm.pinvg[i] = 0.f; }
+        else {
+            // folded BatchNorm of layer l-1 in the log2 domain; xhat = (y - mu) rstd = (z - beta) / gamma with
+            // gamma = a / rstd, beta = b + mu a  (a, b: folded scale / shift)
+            const float a = p.pa[i], b = p.pb[i];
+            sm.pa[i] = a * 1.44269504089f; sm.pb[i] = b * 1.44269504089f;
+            sm.pbeta[i] = b + p.pmu[i] * a; sm.pinvg[i] = p.prstd[i] / a;
+        }
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -341,65 +347,123 @@ tc_bwd_kernel(const TcBwdParams p)
     tc_fence_after_sync();
     const uint32_t tmem_base = sm.tmem_base;
 
+    // ================================ producers: warps 0-7 build G (two layouts), warps 8-11 build X^T ==================
+    // The tile is 4 pixel groups (8 px) x 8 channel groups (16 ch) = 32 blocks of (8 px x 64 B).  A G warp owns 4 blocks (two
+    // sources: dZ and Y), an X warp owns 8.  Loads are software-pipelined in registers: the NEXT tile's loads are issued
+    // before the current tile is transformed, so a producer always has a tile's worth of bytes in flight.
     if (warp < 8) {
-        // ================================ producers: warps 0-3 build G (two layouts), warps 4-7 build X^T ================
-        const bool isG = warp < 4;
-        const int pw = warp & 3, r8 = lane & 7, qd = lane >> 3;
-        int it = 0, s = 0, n = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int r8 = lane & 7, qd = lane >> 3;
+        auto load = [&](int tile, float4 (&va)[4], float4 (&vb)[4]) {
             const int m0 = tile * kPx;
-            // the tile is 4 pixel groups (8 px) x 8 channel groups (16 ch); this warp owns 8 of the 32 blocks.
-            // Every load of the tile is issued before the stage wait (up to 16 x 16 B per thread in flight).
-            float4 va[8], vb[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int blk = pw * 8 + e;
+            for (int e = 0; e < 4; ++e) {
+                const int blk = warp * 4 + e;
                 const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
                 const int m = m0 + px;
                 const bool ok = m < p.M;
-                if (isG) {
-                    va[e] = ok ? *reinterpret_cast<const float4 *>(p.dZ + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    vb[e] = (ok && p.ga) ? *reinterpret_cast<const float4 *>(p.Y + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-                    va[e] = (ok && ch < p.kin) ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                va[e] = ok ? *reinterpret_cast<const float4 *>(p.dZ + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vb[e] = (ok && p.ga) ? *reinterpret_cast<const float4 *>(p.Y + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        auto process = [&](int tile, int s, int n, const float4 (&va)[4], const float4 (&vb)[4]) {
+            const int m0 = tile * kPx;
             mbar_wait(&sm.empty[s], (n & 1) ^ 1);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int blk = pw * 8 + e;
+            for (int e = 0; e < 4; ++e) {
+                const int blk = warp * 4 + e;
                 const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
-                const bool ok = (m0 + px) < p.M;
+                const float4 cA = *reinterpret_cast<const float4 *>(&sm.gA[ch]), cB = *reinterpret_cast<const float4 *>(&sm.gB[ch]),
+                             cC = *reinterpret_cast<const float4 *>(&sm.gC[ch]);
                 float4 o;
-                if (isG) {
-                    const float4 ga = *reinterpret_cast<const float4 *>(&sm.ga[ch]), m1 = *reinterpret_cast<const float4 *>(&sm.m1[ch]),
-                                 m2 = *reinterpret_cast<const float4 *>(&sm.m2[ch]), mu = *reinterpret_cast<const float4 *>(&sm.mu[ch]),
-                                 rs = *reinterpret_cast<const float4 *>(&sm.rstd[ch]);
-                    o.x = ga.x * (va[e].x - m1.x - (vb[e].x - mu.x) * rs.x * m2.x);
-                    o.y = ga.y * (va[e].y - m1.y - (vb[e].y - mu.y) * rs.y * m2.y);
-                    o.z = ga.z * (va[e].z - m1.z - (vb[e].z - mu.z) * rs.z * m2.z);
-                    o.w = ga.w * (va[e].w - m1.w - (vb[e].w - mu.w) * rs.w * m2.w);
-                } else if (p.x_raw) {
-                    o = va[e];
-                } else {
-                    const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
-                    o.x = softplus_log2(fmaf(va[e].x, av.x, bv.x)); o.y = softplus_log2(fmaf(va[e].y, av.y, bv.y));
-                    o.z = softplus_log2(fmaf(va[e].z, av.z, bv.z)); o.w = softplus_log2(fmaf(va[e].w, av.w, bv.w));
-                }
-                if (!ok) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                o.x = fmaf(cA.x, va[e].x, fmaf(cB.x, vb[e].x, cC.x)); o.y = fmaf(cA.y, va[e].y, fmaf(cB.y, vb[e].y, cC.y));
+                o.z = fmaf(cA.z, va[e].z, fmaf(cB.z, vb[e].z, cC.z)); o.w = fmaf(cA.w, va[e].w, fmaf(cB.w, vb[e].w, cC.w));
+                if (m0 + px >= p.M) o = make_float4(0.f, 0.f, 0.f, 0.f);
                 o = to_tf32(o);
-                if (isG) *reinterpret_cast<float4 *>(sm.gk[s] + (ch >> 5) * kGkChunk + sw128_offset(px, (ch & 31) >> 2)) = o;
-                unsigned char *tt = isG ? sm.gt[s] : sm.xt[s];
-                *reinterpret_cast<float *>(tt + tr_offset(ch + 0, px)) = o.x;
-                *reinterpret_cast<float *>(tt + tr_offset(ch + 1, px)) = o.y;
-                *reinterpret_cast<float *>(tt + tr_offset(ch + 2, px)) = o.z;
-                *reinterpret_cast<float *>(tt + tr_offset(ch + 3, px)) = o.w;
+                *reinterpret_cast<float4 *>(sm.gk[s] + (ch >> 5) * kGkChunk + sw128_offset(px, (ch & 31) >> 2)) = o;
+                // rows ch..ch+3 of the transposed tile, column px: (ch & 7) is 0 or 4, so the swizzle unit is (px>>2) ^ ((ch&4) | i)
+                unsigned char *tt = sm.gt[s] + (uint32_t)ch * 128u + (uint32_t)(px & 3) * 4u;
+                const uint32_t u0 = (uint32_t)((px >> 2) ^ (ch & 4));
+                *reinterpret_cast<float *>(tt + 0 * 128 + ((u0 ^ 0u) << 4)) = o.x;
+                *reinterpret_cast<float *>(tt + 1 * 128 + ((u0 ^ 1u) << 4)) = o.y;
+                *reinterpret_cast<float *>(tt + 2 * 128 + ((u0 ^ 2u) << 4)) = o.z;
+                *reinterpret_cast<float *>(tt + 3 * 128 + ((u0 ^ 3u) << 4)) = o.w;
             }
             fence_proxy_async_smem();
             mbar_arrive(&sm.full[s]);
+        };
+        float4 a0[4], a1[4], b0[4], b1[4];
+        int s = 0, n = 0;
+        int tile = blockIdx.x;
+        if (tile < num_tiles) load(tile, a0, b0);
+        while (tile < num_tiles) {
+            const int t1 = tile + gridDim.x;
+            if (t1 < num_tiles) load(t1, a1, b1);
+            process(tile, s, n, a0, b0);
             if (++s == kBStages) { s = 0; ++n; }
+            tile = t1;
+            if (tile >= num_tiles) break;
+            const int t2 = tile + gridDim.x;
+            if (t2 < num_tiles) load(t2, a0, b0);
+            process(tile, s, n, a1, b1);
+            if (++s == kBStages) { s = 0; ++n; }
+            tile = t2;
         }
-    } else if (warp == 8) {
+    } else if (warp < kBwdMmaWarp) {
+        const int r8 = lane & 7, qd = lane >> 3;
+        const int xw = warp - 8;
+        auto load = [&](int tile, float4 (&va)[8]) {
+            const int m0 = tile * kPx;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int blk = xw * 8 + e;
+                const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
+                const int m = m0 + px;
+                va[e] = (m < p.M && ch < p.kin) ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        auto process = [&](int tile, int s, int n, const float4 (&va)[8]) {
+            const int m0 = tile * kPx;
+            mbar_wait(&sm.empty[s], (n & 1) ^ 1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int blk = xw * 8 + e;
+                const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
+                float4 o = va[e];
+                if (!p.x_raw) {
+                    const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
+                    o.x = softplus_log2(fmaf(o.x, av.x, bv.x)); o.y = softplus_log2(fmaf(o.y, av.y, bv.y));
+                    o.z = softplus_log2(fmaf(o.z, av.z, bv.z)); o.w = softplus_log2(fmaf(o.w, av.w, bv.w));
+                }
+                if (m0 + px >= p.M) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                o = to_tf32(o);
+                unsigned char *tt = sm.xt[s] + (uint32_t)ch * 128u + (uint32_t)(px & 3) * 4u;
+                const uint32_t u0 = (uint32_t)((px >> 2) ^ (ch & 4));
+                *reinterpret_cast<float *>(tt + 0 * 128 + ((u0 ^ 0u) << 4)) = o.x;
+                *reinterpret_cast<float *>(tt + 1 * 128 + ((u0 ^ 1u) << 4)) = o.y;
+                *reinterpret_cast<float *>(tt + 2 * 128 + ((u0 ^ 2u) << 4)) = o.z;
+                *reinterpret_cast<float *>(tt + 3 * 128 + ((u0 ^ 3u) << 4)) = o.w;
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(&sm.full[s]);
+        };
+        float4 a0[8], a1[8];
+        int s = 0, n = 0;
+        int tile = blockIdx.x;
+        if (tile < num_tiles) load(tile, a0);
+        while (tile < num_tiles) {
+            const int t1 = tile + gridDim.x;
+            if (t1 < num_tiles) load(t1, a1);
+            process(tile, s, n, a0);
+            if (++s == kBStages) { s = 0; ++n; }
+            tile = t1;
+            if (tile >= num_tiles) break;
+            const int t2 = tile + gridDim.x;
+            if (t2 < num_tiles) load(t2, a0);
+            process(tile, s, n, a1);
+            if (++s == kBStages) { s = 0; ++n; }
+            tile = t2;
+        }
+    } else if (warp == kBwdMmaWarp) {
         // ================================ MMA issuer ================================
         constexpr uint32_t idesc_dgrad = make_idesc_tf32(128, kPx, false, false);
         constexpr uint32_t idesc_wgrad = make_idesc_tf32(128, 128, false, false);
@@ -427,44 +491,61 @@ tc_bwd_kernel(const TcBwdParams p)
             if (++s == kBStages) { s = 0; ++n; }
         }
     } else {
-        // ================================ epilogue: one input channel per thread ================================
+        // ================================ epilogue: one input channel x 16 pixels per thread ================================
+        // 8 warps: warp w reads TMEM lane quarter (w & 3) and pixel half (w - first) >> 2; a thread's BatchNorm scalars are
+        // constants; sigmoid(z_{l-1}) and xhat_{l-1} are recovered from x = softplus(z) in the X^T tile (no global re-read).
+        const int ew = warp - kBwdEpiWarp0;          // 0..7
         const int q = warp & 3;
         const int c = q * 32 + lane;                 // TMEM lane == input channel
-        const int we = warp - 9;                     // 0..3 for the coalesced store phase
-        const float ca = sm.pa[c], cb = sm.pb[c], cmu = sm.pmu[c], crs = sm.prstd[c];
+        const int ph = ew >> 2;                      // pixel half: columns [16 ph, 16 ph + 16)
+        const float cbeta = sm.pbeta[c], cinvg = sm.pinvg[c];
         const bool final_mode = (p.mode == 0 || p.mode == 3);
         const bool cvalid = c < p.kin;
         double d1 = 0.0, d2 = 0.0;
-        int it = 0, s = 0, n = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        int s = 0, n = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = tile * kPx;
-            float v[32], yv[32], ev[32];
-            // independent of the MMA: fetch this channel's Y_{l-1} column (and the running partial sum) first
+            float ev[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int m = m0 + j;
-                yv[j] = (final_mode && cvalid && m < p.M) ? p.Yprev[(size_t)m * p.ldp + c] : 0.f;
+            for (int j = 0; j < 16; ++j) {
+                const int m = m0 + ph * 16 + j;
                 ev[j] = (p.mode >= 2 && cvalid && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
             }
             mbar_wait(&sm.mma_done[s], n & 1);
             tc_fence_after_sync();
-            float *stg = reinterpret_cast<float *>(sm.gk[s]);      // both products have consumed this stage: [32 px][128] staging
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx, v);
+            float v[16];
+            tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx + ph * 16, v);
             tc_fence_before_sync();
             mbar_arrive(&sm.tmem_empty[s]);
+            // x = softplus(z) of this channel's 16 pixels sits in the X^T tile (row c): sigmoid(z) = 1 - e^-x, z = x + ln(sigmoid)
+            float xs[16];
+            if (final_mode) {
+                const unsigned char *xr = sm.xt[s] + (uint32_t)c * 128u;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 t = *reinterpret_cast<const float4 *>(xr + ((((ph * 4 + u) ^ (c & 7))) << 4));
+                    xs[4 * u] = t.x; xs[4 * u + 1] = t.y; xs[4 * u + 2] = t.z; xs[4 * u + 3] = t.w;
+                }
+            }
+            float *stg = reinterpret_cast<float *>(sm.gk[s]);      // both products have consumed this stage: [32 px][128] staging
             float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
                 float dx = v[j] + ev[j];
                 if (final_mode) {
-                    dx *= sigmoid_log2(fmaf(yv[j], ca, cb));
-                    if (m0 + j < p.M) { t1 += dx; t2 = fmaf(dx, (yv[j] - cmu) * crs, t2); }
+                    float em, ls;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(em) : "f"(-1.44269504089f * xs[j]));
+                    const float sg = 1.f - em;
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ls) : "f"(fmaxf(sg, 1e-30f)));
+                    const float z = fmaf(0.69314718056f, ls, xs[j]);
+                    dx *= sg;
+                    if (m0 + ph * 16 + j < p.M) { t1 += dx; t2 = fmaf(dx, (z - cbeta) * cinvg, t2); }
                 }
-                stg[j * 128 + c] = dx;
+                stg[(ph * 16 + j) * 128 + c] = dx;
             }
             d1 += (double)t1; d2 += (double)t2;
-            named_bar_sync(1, 128);
-            for (int r = we * 8; r < we * 8 + 8; ++r) {
+            named_bar_sync(1, 8 * 32);
+            for (int r = ew * 4; r < ew * 4 + 4; ++r) {
                 const int m = m0 + r;
                 if (m >= p.M) break;
                 if (lane * 4 < p.kin)
@@ -474,20 +555,22 @@ tc_bwd_kernel(const TcBwdParams p)
             if (++s == kBStages) { s = 0; ++n; }
         }
         if (final_mode && p.s1) { atomicAdd(&p.s1[c], d1); atomicAdd(&p.s2[c], d2); }
-        // flush the weight-gradient accumulator: lane == output channel; every MMA was covered by the last mma_done wait
+        // flush the weight-gradient accumulator: lane == output channel, two column halves per quarter; every MMA was
+        // covered by the last mma_done wait
         tc_fence_after_sync();
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
+        for (int cc = 0; cc < 2; ++cc) {
             float v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 32, v);
+            const int col0 = (ph * 2 + cc) * 32;
+            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + col0, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-                if (cc * 32 + j < p.kin) atomicAdd(p.dW + (size_t)c * p.lddw + cc * 32 + j, v[j]);
+                if (col0 + j < p.kin) atomicAdd(p.dW + (size_t)c * p.lddw + col0 + j, v[j]);
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, kBwdTmemCols);
+    if (warp == kBwdMmaWarp) tmem_dealloc(tmem_base, kBwdTmemCols);
 }
 
 }  // namespace
