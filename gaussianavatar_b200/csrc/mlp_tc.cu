@@ -524,7 +524,9 @@ tc_bwd_kernel(const TcBwdParams p)
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float4 t = *reinterpret_cast<const float4 *>(xr + ((((ph * 4 + u) ^ (c & 7))) << 4));
-                    xs[4 * u] = t.x; xs[4 * u + 1] = t.y; xs[4 * u + 2] = t.z; xs[4 * u + 3] = t.w;
+                    // the producers stored x + half a TF32 ulp (bit pattern + 0x1000, nothing truncated): undo it -> exact fp32 x
+                    xs[4 * u] = __uint_as_float(__float_as_uint(t.x) - 0x1000u); xs[4 * u + 1] = __uint_as_float(__float_as_uint(t.y) - 0x1000u);
+                    xs[4 * u + 2] = __uint_as_float(__float_as_uint(t.z) - 0x1000u); xs[4 * u + 3] = __uint_as_float(__float_as_uint(t.w) - 0x1000u);
                 }
             }
             float *stg = reinterpret_cast<float *>(sm.gk[s]);      // both products have consumed this stage: [32 px][128] staging
