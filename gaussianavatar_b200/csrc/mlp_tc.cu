@@ -268,7 +268,7 @@ constexpr int kBStages = 3;
 constexpr int kGkChunk = kPx * 128;       // 4 KB: [32 px rows][32 channels]
 constexpr int kGkTile = 4 * kGkChunk;     // 16 KB
 constexpr int kTTile = 128 * 128;         // 16 KB: [128 channel rows][32 px]
-constexpr int kBwdThreads = 21 * 32;      // 8 G-producer warps, 4 X-producer warps, 1 MMA warp, 8 epilogue warps
+constexpr int kBwdThreads = 17 * 32;      // 8 G-producer warps, 4 X-producer warps, 1 MMA warp, 4 epilogue warps (96 regs/thread)
 constexpr int kBwdMmaWarp = 12, kBwdEpiWarp0 = 13;
 constexpr uint32_t kBwdTmemCols = 256;    // [0,128): dW accumulator; 128 + 32 s: dX^T accumulator of stage s
 
@@ -308,8 +308,8 @@ tc_bwd_kernel(const TcBwdParams p)
 
     if (tid == 0) {
         for (int s = 0; s < kBStages; ++s) {
-            mbar_init(&sm.full[s], 12 * 32); mbar_init(&sm.empty[s], 8 * 32);
-            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 8 * 32);
+            mbar_init(&sm.full[s], 12 * 32); mbar_init(&sm.empty[s], 4 * 32);
+            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 4 * 32);
         }
         fence_barrier_init();
     }
@@ -491,13 +491,12 @@ tc_bwd_kernel(const TcBwdParams p)
             if (++s == kBStages) { s = 0; ++n; }
         }
     } else {
-        // ================================ epilogue: one input channel x 16 pixels per thread ================================
-        // 8 warps: warp w reads TMEM lane quarter (w & 3) and pixel half (w - first) >> 2; a thread's BatchNorm scalars are
-        // constants; sigmoid(z_{l-1}) and xhat_{l-1} are recovered from x = softplus(z) in the X^T tile (no global re-read).
-        const int ew = warp - kBwdEpiWarp0;          // 0..7
+        // ================================ epilogue: one input channel per thread ================================
+        // 4 warps (TMEM lane quarter = warp & 3).  A thread's BatchNorm scalars are constants; sigmoid(z_{l-1}) and
+        // xhat_{l-1} are recovered from x = softplus(z) in the X^T tile (no global re-read); 2 x 16 pixels per tile.
+        const int ew = warp - kBwdEpiWarp0;          // 0..3
         const int q = warp & 3;
         const int c = q * 32 + lane;                 // TMEM lane == input channel
-        const int ph = ew >> 2;                      // pixel half: columns [16 ph, 16 ph + 16)
         const float cbeta = sm.pbeta[c], cinvg = sm.pinvg[c];
         const bool final_mode = (p.mode == 0 || p.mode == 3);
         const bool cvalid = c < p.kin;
@@ -505,49 +504,51 @@ tc_bwd_kernel(const TcBwdParams p)
         int s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = tile * kPx;
-            float ev[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int m = m0 + ph * 16 + j;
-                ev[j] = (p.mode >= 2 && cvalid && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
-            }
             mbar_wait(&sm.mma_done[s], n & 1);
             tc_fence_after_sync();
-            float v[16];
-            tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx + ph * 16, v);
-            tc_fence_before_sync();
-            mbar_arrive(&sm.tmem_empty[s]);
-            // x = softplus(z) of this channel's 16 pixels sits in the X^T tile (row c): sigmoid(z) = 1 - e^-x, z = x + ln(sigmoid)
-            float xs[16];
-            if (final_mode) {
-                const unsigned char *xr = sm.xt[s] + (uint32_t)c * 128u;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float4 t = *reinterpret_cast<const float4 *>(xr + ((((ph * 4 + u) ^ (c & 7))) << 4));
-                    // the producers stored x + half a TF32 ulp (bit pattern + 0x1000, nothing truncated): undo it -> exact fp32 x
-                    xs[4 * u] = __uint_as_float(__float_as_uint(t.x) - 0x1000u); xs[4 * u + 1] = __uint_as_float(__float_as_uint(t.y) - 0x1000u);
-                    xs[4 * u + 2] = __uint_as_float(__float_as_uint(t.z) - 0x1000u); xs[4 * u + 3] = __uint_as_float(__float_as_uint(t.w) - 0x1000u);
-                }
-            }
             float *stg = reinterpret_cast<float *>(sm.gk[s]);      // both products have consumed this stage: [32 px][128] staging
             float t1 = 0.f, t2 = 0.f;
+#pragma unroll 1
+            for (int ph = 0; ph < 2; ++ph) {
+                float ev[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float dx = v[j] + ev[j];
-                if (final_mode) {
-                    float em, ls;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(em) : "f"(-1.44269504089f * xs[j]));
-                    const float sg = 1.f - em;
-                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ls) : "f"(fmaxf(sg, 1e-30f)));
-                    const float z = fmaf(0.69314718056f, ls, xs[j]);
-                    dx *= sg;
-                    if (m0 + ph * 16 + j < p.M) { t1 += dx; t2 = fmaf(dx, (z - cbeta) * cinvg, t2); }
+                for (int j = 0; j < 16; ++j) {
+                    const int m = m0 + ph * 16 + j;
+                    ev[j] = (p.mode >= 2 && cvalid && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
                 }
-                stg[(ph * 16 + j) * 128 + c] = dx;
+                float v[16];
+                tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx + ph * 16, v);
+                float xs[16];
+                if (final_mode) {
+                    const unsigned char *xr = sm.xt[s] + (uint32_t)c * 128u;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 t = *reinterpret_cast<const float4 *>(xr + ((((ph * 4 + u) ^ (c & 7))) << 4));
+                        // the producers stored x + half a TF32 ulp (bit pattern + 0x1000, nothing truncated): undo it -> exact fp32 x
+                        xs[4 * u] = __uint_as_float(__float_as_uint(t.x) - 0x1000u); xs[4 * u + 1] = __uint_as_float(__float_as_uint(t.y) - 0x1000u);
+                        xs[4 * u + 2] = __uint_as_float(__float_as_uint(t.z) - 0x1000u); xs[4 * u + 3] = __uint_as_float(__float_as_uint(t.w) - 0x1000u);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float dx = v[j] + ev[j];
+                    if (final_mode) {
+                        float em, ls;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(em) : "f"(-1.44269504089f * xs[j]));
+                        const float sg = 1.f - em;
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ls) : "f"(fmaxf(sg, 1e-30f)));
+                        const float z = fmaf(0.69314718056f, ls, xs[j]);
+                        dx *= sg;
+                        if (m0 + ph * 16 + j < p.M) { t1 += dx; t2 = fmaf(dx, (z - cbeta) * cinvg, t2); }
+                    }
+                    stg[(ph * 16 + j) * 128 + c] = dx;
+                }
             }
+            tc_fence_before_sync();
+            mbar_arrive(&sm.tmem_empty[s]);
             d1 += (double)t1; d2 += (double)t2;
-            named_bar_sync(1, 8 * 32);
-            for (int r = ew * 4; r < ew * 4 + 4; ++r) {
+            named_bar_sync(1, 4 * 32);
+            for (int r = ew * 8; r < ew * 8 + 8; ++r) {
                 const int m = m0 + r;
                 if (m >= p.M) break;
                 if (lane * 4 < p.kin)
@@ -557,17 +558,15 @@ tc_bwd_kernel(const TcBwdParams p)
             if (++s == kBStages) { s = 0; ++n; }
         }
         if (final_mode && p.s1) { atomicAdd(&p.s1[c], d1); atomicAdd(&p.s2[c], d2); }
-        // flush the weight-gradient accumulator: lane == output channel, two column halves per quarter; every MMA was
-        // covered by the last mma_done wait
+        // flush the weight-gradient accumulator: lane == output channel; every MMA was covered by the last mma_done wait
         tc_fence_after_sync();
 #pragma unroll 1
-        for (int cc = 0; cc < 2; ++cc) {
-            float v[32];
-            const int col0 = (ph * 2 + cc) * 32;
-            tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + col0, v);
+        for (int cc = 0; cc < 8; ++cc) {
+            float v[16];
+            tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 16, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.kin) atomicAdd(p.dW + (size_t)c * p.lddw + col0 + j, v[j]);
+            for (int j = 0; j < 16; ++j)
+                if (cc * 16 + j < p.kin) atomicAdd(p.dW + (size_t)c * p.lddw + cc * 16 + j, v[j]);
         }
     }
     tc_fence_before_sync();
