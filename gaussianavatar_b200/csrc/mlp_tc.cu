@@ -26,7 +26,8 @@ constexpr int kBM = 128, kBN = 128;
 constexpr int kChunkBytes = kBM * 128;          // one 32-channel chunk of a 128-row tile: 16 KB
 constexpr int kMaxChunks = 4;                    // K <= 128
 constexpr int kStageBytes = kMaxChunks * kChunkBytes;   // 64 KB
-constexpr int kTcThreads = 13 * 32;     // 8 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int kTcThreads = 21 * 32;     // 16 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int kFwdMmaWarp = 16, kFwdEpiWarp0 = 17;
 constexpr uint32_t kTmemCols = 256;
 
 struct TcFwdParams {
@@ -61,12 +62,12 @@ tc_fwd_kernel(const TcFwdParams p)
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm.full[s], 256); mbar_init(&sm.empty[s], 128);
+            mbar_init(&sm.full[s], 16 * 32); mbar_init(&sm.empty[s], 128);
             mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 128);
         }
         fence_barrier_init();
     }
-    if (warp == 8) tmem_alloc(&sm.tmem_base, kTmemCols);
+    if (warp == kFwdMmaWarp) tmem_alloc(&sm.tmem_base, kTmemCols);
     // weights -> shared, K-major, 128-byte swizzle
     for (int i = tid; i < kBN * (p.K / 4); i += kTcThreads) {
         const int n = i / (p.K / 4), q = i % (p.K / 4);
@@ -83,10 +84,11 @@ tc_fwd_kernel(const TcFwdParams p)
     tc_fence_after_sync();
     const uint32_t tmem_base = sm.tmem_base;
 
-    if (warp < 8) {
+    if (warp < kFwdMmaWarp) {
         // ================================ producers ================================
-        // warp w owns channel chunk c = w & 3 (its BatchNorm coefficients live in registers) and row groups 2i + (w >> 2);
-        // one warp instruction = 4 rows x 128 B.  All 16 loads of a tile are in flight before the stage is even free.
+        // warp w owns channel chunk c = w & 3 (its BatchNorm coefficients live in registers) and row groups 4i + (w >> 2);
+        // one warp instruction = 4 rows x 128 B.  Loads are software-pipelined in registers: the NEXT tile's 8 loads are
+        // issued before the current tile is transformed.
         const int rl = lane >> 3, u = lane & 7;
         const int c = warp & 3, rg0 = warp >> 2;
         const int k = c * 32 + u * 4;
@@ -98,22 +100,21 @@ tc_fwd_kernel(const TcFwdParams p)
             const float L2E = 1.44269504089f;
             av.x *= L2E; av.y *= L2E; av.z *= L2E; av.w *= L2E; bv.x *= L2E; bv.y *= L2E; bv.z *= L2E; bv.w *= L2E;
         }
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int s = it & 1, n = it >> 1;
+        auto load = [&](int tile, float4 (&v)[8]) {
             const int m0 = tile * kBM;
-            float4 v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int m = m0 + (2 * i + rg0) * 4 + rl;
+            for (int i = 0; i < 8; ++i) {
+                const int m = m0 + (4 * i + rg0) * 4 + rl;
                 v[i] = (kin && m < p.M) ? *reinterpret_cast<const float4 *>(p.X + (size_t)m * p.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+        };
+        auto process = [&](int s, int n, const float4 (&v)[8]) {
             mbar_wait(&sm.empty[s], (n & 1) ^ 1);
             unsigned char *dst = sm.a[s] + c * kChunkBytes;
             if (c * 32 < p.K) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int r = (2 * i + rg0) * 4 + rl;
+                for (int i = 0; i < 8; ++i) {
+                    const int r = (4 * i + rg0) * 4 + rl;
                     float4 x = v[i];
                     if (act) {
                         x.x = softplus_log2(fmaf(x.x, av.x, bv.x)); x.y = softplus_log2(fmaf(x.y, av.y, bv.y));
@@ -124,8 +125,23 @@ tc_fwd_kernel(const TcFwdParams p)
             }
             fence_proxy_async_smem();
             mbar_arrive(&sm.full[s]);
+        };
+        float4 v0[8], v1[8];
+        int it = 0;
+        int tile = blockIdx.x;
+        if (tile < num_tiles) load(tile, v0);
+        while (tile < num_tiles) {
+            const int t1 = tile + gridDim.x;
+            if (t1 < num_tiles) load(t1, v1);
+            process(it & 1, it >> 1, v0);
+            ++it; tile = t1;
+            if (tile >= num_tiles) break;
+            const int t2 = tile + gridDim.x;
+            if (t2 < num_tiles) load(t2, v0);
+            process(it & 1, it >> 1, v1);
+            ++it; tile = t2;
         }
-    } else if (warp == 8) {
+    } else if (warp == kFwdMmaWarp) {
         // ================================ MMA issuer ================================
         constexpr uint32_t idesc = make_idesc_tf32(kBM, kBN, false, false);
         const uint32_t w_addr = smem_u32(sm.w);
@@ -151,7 +167,7 @@ tc_fwd_kernel(const TcFwdParams p)
         // ================================ epilogue ================================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;               // tile row == TMEM lane
-        const int et = (warp - 9) * 32 + lane;       // 0..127: channel owned for the statistics
+        const int et = (warp - kFwdEpiWarp0) * 32 + lane;   // 0..127: channel owned for the statistics
         double dsum = 0.0, dsq = 0.0;
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -176,7 +192,7 @@ tc_fwd_kernel(const TcFwdParams p)
             mbar_arrive(&sm.tmem_empty[s]);          // accumulator drained
             named_bar_sync(1, 128);
             // coalesced row stores (each warp: 32 rows, one 512-byte row per instruction)
-            const int wr = warp - 9;
+            const int wr = warp - kFwdEpiWarp0;
             for (int r = wr * 32; r < wr * 32 + 32; ++r) {
                 const int m = m0 + r;
                 if (m >= p.M) break;
@@ -206,7 +222,7 @@ tc_fwd_kernel(const TcFwdParams p)
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == kFwdMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace
