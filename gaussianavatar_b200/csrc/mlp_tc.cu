@@ -152,12 +152,17 @@ tc_fwd_kernel(const TcFwdParams p)
             mbar_wait(&sm.tmem_empty[s], (n & 1) ^ 1);
             tc_fence_after_sync();
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(sm.a[s]);
-                const int nk = p.K / 8;
-                for (int k = 0; k < nk; ++k) {
-                    const uint32_t off = (uint32_t)(k >> 2) * kChunkBytes + (uint32_t)(k & 3) * 32u;
-                    mma_tf32(tmem_base + (uint32_t)s * kBN, make_smem_desc(a_addr + off, 16, 1024), make_smem_desc(w_addr + off, 16, 1024), idesc,
-                             k > 0);
+                constexpr uint32_t hi = desc_hi(1024);
+                const uint32_t a_lo = desc_lo(smem_u32(sm.a[s]), 16), w_lo = desc_lo(w_addr, 16);
+                const uint32_t d = tmem_base + (uint32_t)s * kBN;
+                const int nk = p.K / 8;           // 16 (K = 128) or 9 (K = 72)
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k < nk) {
+                        constexpr uint32_t kChunk16 = kChunkBytes >> 4;
+                        const uint32_t off = (uint32_t)(k >> 2) * kChunk16 + (uint32_t)(k & 3) * 2u;      // byte offset >> 4
+                        mma_tf32_lohi(d, a_lo + off, w_lo + off, hi, idesc, k > 0);
+                    }
                 }
                 mma_commit(&sm.mma_done[s]);
             }
@@ -490,17 +495,19 @@ tc_bwd_kernel(const TcBwdParams p)
             mbar_wait(&sm.tmem_empty[s], (n & 1) ^ 1);
             tc_fence_after_sync();
             if (lane == 0) {
-                const uint32_t gk_addr = smem_u32(sm.gk[s]), gt_addr = smem_u32(sm.gt[s]), xt_addr = smem_u32(sm.xt[s]);
+                constexpr uint32_t hi = desc_hi(1024);
+                const uint32_t wt_lo = desc_lo(wt_addr, 16), gk_lo = desc_lo(smem_u32(sm.gk[s]), 16), gt_lo = desc_lo(smem_u32(sm.gt[s]), 16),
+                               xt_lo = desc_lo(smem_u32(sm.xt[s]), 16);
+                const uint32_t d_dx = tmem_base + 128 + (uint32_t)s * kPx;
                 // dX^T[in, px] = sum_out W^T[in, out] G[px, out]: 16 steps of 8 output channels
-#pragma unroll 1
+#pragma unroll
                 for (int k = 0; k < 16; ++k)
-                    mma_tf32(tmem_base + 128 + (uint32_t)s * kPx, make_smem_desc(wt_addr + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024),
-                             make_smem_desc(gk_addr + (k >> 2) * kGkChunk + (k & 3) * 32, 16, 1024), idesc_dgrad, k > 0);
+                    mma_tf32_lohi(d_dx, wt_lo + (uint32_t)(k >> 2) * ((128 * 128) >> 4) + (uint32_t)(k & 3) * 2u,
+                                  gk_lo + (uint32_t)(k >> 2) * (kGkChunk >> 4) + (uint32_t)(k & 3) * 2u, hi, idesc_dgrad, k > 0);
                 // dW[out, in] += sum_px G^T[out, px] X^T[in, px]: 4 steps of 8 pixels
-#pragma unroll 1
+#pragma unroll
                 for (int j = 0; j < kPx / 8; ++j)
-                    mma_tf32(tmem_base, make_smem_desc(gt_addr + j * 32, 16, 1024), make_smem_desc(xt_addr + j * 32, 16, 1024), idesc_wgrad,
-                             (it > 0) || (j > 0));
+                    mma_tf32_lohi(tmem_base, gt_lo + (uint32_t)j * 2u, xt_lo + (uint32_t)j * 2u, hi, idesc_wgrad, (it > 0) || (j > 0));
                 mma_commit(&sm.mma_done[s]);
             }
             __syncwarp();
