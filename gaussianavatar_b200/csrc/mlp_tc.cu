@@ -62,8 +62,8 @@ tc_fwd_kernel(const TcFwdParams p)
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm.full[s], 16 * 32); mbar_init(&sm.empty[s], 128);
-            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 128);
+            mbar_init(&sm.full[s], 16); mbar_init(&sm.empty[s], 4);        // arrivals are per WARP (warp_arrive)
+            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 4);
         }
         fence_barrier_init();
     }
@@ -109,7 +109,7 @@ tc_fwd_kernel(const TcFwdParams p)
             }
         };
         auto process = [&](int s, int n, const float4 (&v)[8]) {
-            mbar_wait(&sm.empty[s], (n & 1) ^ 1);
+            warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
             unsigned char *dst = sm.a[s] + c * kChunkBytes;
             if (c * 32 < p.K) {
 #pragma unroll
@@ -124,7 +124,7 @@ tc_fwd_kernel(const TcFwdParams p)
                 }
             }
             fence_proxy_async_smem();
-            mbar_arrive(&sm.full[s]);
+            warp_arrive(&sm.full[s], lane);
         };
         float4 v0[8], v1[8];
         int it = 0;
@@ -148,8 +148,8 @@ tc_fwd_kernel(const TcFwdParams p)
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1, n = it >> 1;
-            mbar_wait(&sm.full[s], n & 1);
-            mbar_wait(&sm.tmem_empty[s], (n & 1) ^ 1);
+            warp_wait(&sm.full[s], n & 1, lane);
+            warp_wait(&sm.tmem_empty[s], (n & 1) ^ 1, lane);
             tc_fence_after_sync();
             if (lane == 0) {
                 constexpr uint32_t hi = desc_hi(1024);
@@ -178,7 +178,7 @@ tc_fwd_kernel(const TcFwdParams p)
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1, n = it >> 1;
             const int m0 = tile * kBM;
-            mbar_wait(&sm.mma_done[s], n & 1);
+            warp_wait(&sm.mma_done[s], n & 1, lane);
             tc_fence_after_sync();
             unsigned char *stg = sm.a[s];            // the MMA has finished reading this stage: reuse it as staging
 #pragma unroll 1
@@ -194,7 +194,7 @@ tc_fwd_kernel(const TcFwdParams p)
                 }
             }
             tc_fence_before_sync();
-            mbar_arrive(&sm.tmem_empty[s]);          // accumulator drained
+            warp_arrive(&sm.tmem_empty[s], lane);          // accumulator drained
             named_bar_sync(1, 128);
             // coalesced row stores (each warp: 32 rows, one 512-byte row per instruction)
             const int wr = warp - kFwdEpiWarp0;
@@ -221,7 +221,7 @@ tc_fwd_kernel(const TcFwdParams p)
                 }
                 dsum += (double)cs; dsq += (double)cq;
             }
-            mbar_arrive(&sm.empty[s]);               // staging consumed: the producers may refill this stage
+            warp_arrive(&sm.empty[s], lane);               // staging consumed: the producers may refill this stage
         }
         if (p.sum) { atomicAdd(&p.sum[et], dsum); atomicAdd(&p.sumsq[et], dsq); }
     }
@@ -329,8 +329,8 @@ tc_bwd_kernel(const TcBwdParams p)
 
     if (tid == 0) {
         for (int s = 0; s < kBStages; ++s) {
-            mbar_init(&sm.full[s], 12 * 32); mbar_init(&sm.empty[s], 4 * 32);
-            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 4 * 32);
+            mbar_init(&sm.full[s], 12); mbar_init(&sm.empty[s], 4);        // arrivals are per WARP (warp_arrive)
+            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 4);
         }
         fence_barrier_init();
     }
@@ -388,7 +388,7 @@ tc_bwd_kernel(const TcBwdParams p)
         };
         auto process = [&](int tile, int s, int n, const float4 (&va)[4], const float4 (&vb)[4]) {
             const int m0 = tile * kPx;
-            mbar_wait(&sm.empty[s], (n & 1) ^ 1);
+            warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int blk = warp * 4 + e;
@@ -410,7 +410,7 @@ tc_bwd_kernel(const TcBwdParams p)
                 *reinterpret_cast<float *>(tt + 3 * 128 + ((u0 ^ 3u) << 4)) = o.w;
             }
             fence_proxy_async_smem();
-            mbar_arrive(&sm.full[s]);
+            warp_arrive(&sm.full[s], lane);
         };
         float4 a0[4], a1[4], b0[4], b1[4];
         int s = 0, n = 0;
@@ -444,7 +444,7 @@ tc_bwd_kernel(const TcBwdParams p)
         };
         auto process = [&](int tile, int s, int n, const float4 (&va)[8]) {
             const int m0 = tile * kPx;
-            mbar_wait(&sm.empty[s], (n & 1) ^ 1);
+            warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int blk = xw * 8 + e;
@@ -465,7 +465,7 @@ tc_bwd_kernel(const TcBwdParams p)
                 *reinterpret_cast<float *>(tt + 3 * 128 + ((u0 ^ 3u) << 4)) = o.w;
             }
             fence_proxy_async_smem();
-            mbar_arrive(&sm.full[s]);
+            warp_arrive(&sm.full[s], lane);
         };
         float4 a0[8], a1[8];
         int s = 0, n = 0;
@@ -491,8 +491,8 @@ tc_bwd_kernel(const TcBwdParams p)
         const uint32_t wt_addr = smem_u32(sm.wt);
         int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            mbar_wait(&sm.full[s], n & 1);
-            mbar_wait(&sm.tmem_empty[s], (n & 1) ^ 1);
+            warp_wait(&sm.full[s], n & 1, lane);
+            warp_wait(&sm.tmem_empty[s], (n & 1) ^ 1, lane);
             tc_fence_after_sync();
             if (lane == 0) {
                 constexpr uint32_t hi = desc_hi(1024);
@@ -527,7 +527,7 @@ tc_bwd_kernel(const TcBwdParams p)
         int s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = tile * kPx;
-            mbar_wait(&sm.mma_done[s], n & 1);
+            warp_wait(&sm.mma_done[s], n & 1, lane);
             tc_fence_after_sync();
             float *stg = reinterpret_cast<float *>(sm.gk[s]);      // both products have consumed this stage: [32 px][128] staging
             float t1 = 0.f, t2 = 0.f;
@@ -568,7 +568,7 @@ tc_bwd_kernel(const TcBwdParams p)
                 }
             }
             tc_fence_before_sync();
-            mbar_arrive(&sm.tmem_empty[s]);
+            warp_arrive(&sm.tmem_empty[s], lane);
             d1 += (double)t1; d2 += (double)t2;
             named_bar_sync(1, 4 * 32);
             for (int r = ew * 8; r < ew * 8 + 8; ++r) {
@@ -577,7 +577,7 @@ tc_bwd_kernel(const TcBwdParams p)
                 if (lane * 4 < p.kin)
                     *reinterpret_cast<float4 *>(p.dZprev + (size_t)m * p.ldo + lane * 4) = *reinterpret_cast<const float4 *>(stg + r * 128 + lane * 4);
             }
-            mbar_arrive(&sm.empty[s]);
+            warp_arrive(&sm.empty[s], lane);
             if (++s == kBStages) { s = 0; ++n; }
         }
         if (final_mode && p.s1) { atomicAdd(&p.s1[c], d1); atomicAdd(&p.s2[c], d2); }
