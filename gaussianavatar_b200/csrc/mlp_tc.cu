@@ -26,8 +26,8 @@ constexpr int kBM = 128, kBN = 128;
 constexpr int kChunkBytes = kBM * 128;          // one 32-channel chunk of a 128-row tile: 16 KB
 constexpr int kMaxChunks = 4;                    // K <= 128
 constexpr int kStageBytes = kMaxChunks * kChunkBytes;   // 64 KB
-constexpr int kTcThreads = 21 * 32;     // 16 producer warps, 1 MMA warp, 4 epilogue warps
-constexpr int kFwdMmaWarp = 16, kFwdEpiWarp0 = 17;
+constexpr int kTcThreads = 13 * 32;     // 8 producer warps, 1 MMA warp, 4 epilogue warps
+constexpr int kFwdMmaWarp = 8, kFwdEpiWarp0 = 9;
 constexpr uint32_t kTmemCols = 256;
 
 struct TcFwdParams {
@@ -62,7 +62,7 @@ tc_fwd_kernel(const TcFwdParams p)
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm.full[s], 16); mbar_init(&sm.empty[s], 4);        // arrivals are per WARP (warp_arrive)
+            mbar_init(&sm.full[s], 8); mbar_init(&sm.empty[s], 4);         // arrivals are per WARP (warp_arrive)
             mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 4);
         }
         fence_barrier_init();
@@ -86,9 +86,9 @@ tc_fwd_kernel(const TcFwdParams p)
 
     if (warp < kFwdMmaWarp) {
         // ================================ producers ================================
-        // warp w owns channel chunk c = w & 3 (its BatchNorm coefficients live in registers) and row groups 4i + (w >> 2);
-        // one warp instruction = 4 rows x 128 B.  Loads are software-pipelined in registers: the NEXT tile's 8 loads are
-        // issued before the current tile is transformed.
+        // warp w owns channel chunk c = w & 3 (its BatchNorm coefficients live in registers) and row groups 2i + (w >> 2);
+        // one warp instruction = 4 rows x 128 B.  Rolling software pipeline: as soon as row group i of the current tile has been
+        // consumed, row group i of the NEXT tile is loaded into the same register, so 16 loads per thread stay in flight.
         const int rl = lane >> 3, u = lane & 7;
         const int c = warp & 3, rg0 = warp >> 2;
         const int k = c * 32 + u * 4;
@@ -100,46 +100,41 @@ tc_fwd_kernel(const TcFwdParams p)
             const float L2E = 1.44269504089f;
             av.x *= L2E; av.y *= L2E; av.z *= L2E; av.w *= L2E; bv.x *= L2E; bv.y *= L2E; bv.z *= L2E; bv.w *= L2E;
         }
-        auto load = [&](int tile, float4 (&v)[8]) {
-            const int m0 = tile * kBM;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int m = m0 + (4 * i + rg0) * 4 + rl;
-                v[i] = (kin && m < p.M) ? *reinterpret_cast<const float4 *>(p.X + (size_t)m * p.ldx + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        const int M = p.M, ldx = p.ldx;
+        const int r0 = rg0 * 4 + rl;                                 // row of group i: r0 + 8 i  ->  (r & 7) == (r0 & 7) for every i
+        const float *x0 = p.X + (size_t)r0 * ldx + k;
+        const size_t tile_stride = (size_t)kBM * ldx;
+        const uint32_t soff = (uint32_t)c * kChunkBytes + sw128_offset(r0, u);      // + i * 8 * 128
+        const bool chunk_used = c * 32 < p.K;
+        auto ldrow = [&](int tile, int i, float4 &v) {
+            const bool ok = kin && (tile * kBM + r0 + 8 * i < M);
+            v = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)tile * tile_stride + (size_t)(8 * i) * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        auto process = [&](int s, int n, const float4 (&v)[8]) {
-            warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
-            unsigned char *dst = sm.a[s] + c * kChunkBytes;
-            if (c * 32 < p.K) {
+        float4 v[16];
+        const int gstep = gridDim.x;
+        int tile = blockIdx.x;
+        if (tile < num_tiles) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = (4 * i + rg0) * 4 + rl;
-                    float4 x = v[i];
-                    if (act) {
-                        x.x = softplus_log2(fmaf(x.x, av.x, bv.x)); x.y = softplus_log2(fmaf(x.y, av.y, bv.y));
-                        x.z = softplus_log2(fmaf(x.z, av.z, bv.z)); x.w = softplus_log2(fmaf(x.w, av.w, bv.w));
-                    }
-                    *reinterpret_cast<float4 *>(dst + sw128_offset(r, u)) = to_tf32(x);
+            for (int i = 0; i < 16; ++i) ldrow(tile, i, v[i]);
+        }
+        for (int it = 0; tile < num_tiles; tile += gstep, ++it) {
+            const int s = it & 1, n = it >> 1;
+            const int next = tile + gstep;
+            const bool has_next = next < num_tiles;
+            warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
+            unsigned char *dst = sm.a[s] + soff;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float4 x = v[i];
+                if (has_next) ldrow(next, i, v[i]);
+                if (act) {
+                    x.x = softplus_log2(fmaf(x.x, av.x, bv.x)); x.y = softplus_log2(fmaf(x.y, av.y, bv.y));
+                    x.z = softplus_log2(fmaf(x.z, av.z, bv.z)); x.w = softplus_log2(fmaf(x.w, av.w, bv.w));
                 }
+                if (chunk_used) *reinterpret_cast<float4 *>(dst + i * 1024) = to_tf32(x);
             }
             fence_proxy_async_smem();
             warp_arrive(&sm.full[s], lane);
-        };
-        float4 v0[8], v1[8];
-        int it = 0;
-        int tile = blockIdx.x;
-        if (tile < num_tiles) load(tile, v0);
-        while (tile < num_tiles) {
-            const int t1 = tile + gridDim.x;
-            if (t1 < num_tiles) load(t1, v1);
-            process(it & 1, it >> 1, v0);
-            ++it; tile = t1;
-            if (tile >= num_tiles) break;
-            const int t2 = tile + gridDim.x;
-            if (t2 < num_tiles) load(t2, v0);
-            process(it & 1, it >> 1, v1);
-            ++it; tile = t2;
         }
     } else if (warp == kFwdMmaWarp) {
         // ================================ MMA issuer ================================
@@ -369,120 +364,119 @@ tc_bwd_kernel(const TcBwdParams p)
     const uint32_t tmem_base = sm.tmem_base;
 
     // ================================ producers: warps 0-7 build G (two layouts), warps 8-11 build X^T ==================
-    // The tile is 4 pixel groups (8 px) x 8 channel groups (16 ch) = 32 blocks of (8 px x 64 B).  A G warp owns 4 blocks (two
-    // sources: dZ and Y), an X warp owns 8.  Loads are software-pipelined in registers: the NEXT tile's loads are issued
-    // before the current tile is transformed, so a producer always has a tile's worth of bytes in flight.
+    // The tile is 4 pixel groups (8 px) x 8 channel groups (16 ch) = 32 blocks of (8 px x 64 B).  A G warp owns the 4 pixel
+    // groups of ONE channel group (so its BatchNorm coefficients are thread constants), an X warp owns two channel groups.
+    // Loads are software-pipelined in registers (the NEXT tile's loads are issued before the current tile is transformed),
+    // and every global / shared offset is a thread constant plus a compile-time term: the loops below are almost pure
+    // LDG / FFMA / STS (the first version of this kernel spent 75% of its issue slots on address and predicate arithmetic).
+    const int M = p.M;
     if (warp < 8) {
         const int r8 = lane & 7, qd = lane >> 3;
-        auto load = [&](int tile, float4 (&va)[4], float4 (&vb)[4]) {
-            const int m0 = tile * kPx;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int blk = warp * 4 + e;
-                const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
-                const int m = m0 + px;
-                const bool ok = m < p.M;
-                va[e] = ok ? *reinterpret_cast<const float4 *>(p.dZ + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-                vb[e] = (ok && p.ga) ? *reinterpret_cast<const float4 *>(p.Y + (size_t)m * p.ldg + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        const int ch = warp * 16 + qd * 4;                                   // this thread's 4 output channels (all tiles, all blocks)
+        const float4 cA = *reinterpret_cast<const float4 *>(&sm.gA[ch]), cB = *reinterpret_cast<const float4 *>(&sm.gB[ch]),
+                     cC = *reinterpret_cast<const float4 *>(&sm.gC[ch]);
+        const int ldg = p.ldg;
+        const bool has_y = p.ga != nullptr;
+        const float *dz0 = p.dZ + (size_t)r8 * ldg + ch, *y0 = (has_y ? p.Y : p.dZ) + (size_t)r8 * ldg + ch;   // block e adds e*8 rows
+        const size_t tile_stride = (size_t)kPx * ldg;
+        // shared offsets: block e is pixel px = e*8 + r8  ->  px & 7 == r8, px >> 2 == 2e + (r8 >> 2), px & 3 == r8 & 3
+        const uint32_t gk_off = (uint32_t)(ch >> 5) * kGkChunk + (uint32_t)r8 * 128u + (uint32_t)((((ch & 31) >> 2) ^ r8) << 4);   // + e*1024
+        const uint32_t gt_off = (uint32_t)ch * 128u + (uint32_t)(r8 & 3) * 4u;                                               // + i*128 + unit
+        const uint32_t t0s = (uint32_t)((r8 >> 2) ^ (ch & 4)) << 4;          // unit << 4 = t0s ^ ((2e ^ i) << 4)
+
+        // Rolling software pipeline: as soon as block e of the current tile has been consumed, block e of the NEXT tile is
+        // loaded into the same registers, so a tile's worth of loads is always in flight with a single register set.
+        auto ldblk = [&](int tile, int e, float4 &za, float4 &ya) {
+            const float *pz = dz0 + (size_t)tile * tile_stride + (size_t)(e * 8) * ldg;
+            const float *py = y0 + (size_t)tile * tile_stride + (size_t)(e * 8) * ldg;
+            const bool ok = tile * kPx + e * 8 + r8 < M;
+            za = ok ? *reinterpret_cast<const float4 *>(pz) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ya = ok ? *reinterpret_cast<const float4 *>(py) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        auto process = [&](int tile, int s, int n, const float4 (&va)[4], const float4 (&vb)[4]) {
-            const int m0 = tile * kPx;
+        float4 va[4], vb[4];
+        int s = 0, n = 0;
+        const int gstep = gridDim.x;
+        int tile = blockIdx.x;
+        if (tile < num_tiles) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) ldblk(tile, e, va[e], vb[e]);
+        }
+        for (; tile < num_tiles; tile += gstep) {
+            const int next = tile + gstep;
+            const bool has_next = next < num_tiles;
             warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
+            unsigned char *gk = sm.gk[s] + gk_off, *gt = sm.gt[s] + gt_off;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int blk = warp * 4 + e;
-                const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
-                const float4 cA = *reinterpret_cast<const float4 *>(&sm.gA[ch]), cB = *reinterpret_cast<const float4 *>(&sm.gB[ch]),
-                             cC = *reinterpret_cast<const float4 *>(&sm.gC[ch]);
                 float4 o;
                 o.x = fmaf(cA.x, va[e].x, fmaf(cB.x, vb[e].x, cC.x)); o.y = fmaf(cA.y, va[e].y, fmaf(cB.y, vb[e].y, cC.y));
                 o.z = fmaf(cA.z, va[e].z, fmaf(cB.z, vb[e].z, cC.z)); o.w = fmaf(cA.w, va[e].w, fmaf(cB.w, vb[e].w, cC.w));
-                if (m0 + px >= p.M) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tile * kPx + e * 8 + r8 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_next) ldblk(next, e, va[e], vb[e]);
                 o = to_tf32(o);
-                *reinterpret_cast<float4 *>(sm.gk[s] + (ch >> 5) * kGkChunk + sw128_offset(px, (ch & 31) >> 2)) = o;
-                // rows ch..ch+3 of the transposed tile, column px: (ch & 7) is 0 or 4, so the swizzle unit is (px>>2) ^ ((ch&4) | i)
-                unsigned char *tt = sm.gt[s] + (uint32_t)ch * 128u + (uint32_t)(px & 3) * 4u;
-                const uint32_t u0 = (uint32_t)((px >> 2) ^ (ch & 4));
-                *reinterpret_cast<float *>(tt + 0 * 128 + ((u0 ^ 0u) << 4)) = o.x;
-                *reinterpret_cast<float *>(tt + 1 * 128 + ((u0 ^ 1u) << 4)) = o.y;
-                *reinterpret_cast<float *>(tt + 2 * 128 + ((u0 ^ 2u) << 4)) = o.z;
-                *reinterpret_cast<float *>(tt + 3 * 128 + ((u0 ^ 3u) << 4)) = o.w;
+                *reinterpret_cast<float4 *>(gk + e * 1024) = o;
+                *reinterpret_cast<float *>(gt + 0 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 0) << 4))) = o.x;
+                *reinterpret_cast<float *>(gt + 1 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 1) << 4))) = o.y;
+                *reinterpret_cast<float *>(gt + 2 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 2) << 4))) = o.z;
+                *reinterpret_cast<float *>(gt + 3 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 3) << 4))) = o.w;
             }
             fence_proxy_async_smem();
             warp_arrive(&sm.full[s], lane);
-        };
-        float4 a0[4], a1[4], b0[4], b1[4];
-        int s = 0, n = 0;
-        int tile = blockIdx.x;
-        if (tile < num_tiles) load(tile, a0, b0);
-        while (tile < num_tiles) {
-            const int t1 = tile + gridDim.x;
-            if (t1 < num_tiles) load(t1, a1, b1);
-            process(tile, s, n, a0, b0);
             if (++s == kBStages) { s = 0; ++n; }
-            tile = t1;
-            if (tile >= num_tiles) break;
-            const int t2 = tile + gridDim.x;
-            if (t2 < num_tiles) load(t2, a0, b0);
-            process(tile, s, n, a1, b1);
-            if (++s == kBStages) { s = 0; ++n; }
-            tile = t2;
         }
     } else if (warp < kBwdMmaWarp) {
         const int r8 = lane & 7, qd = lane >> 3;
         const int xw = warp - 8;
-        auto load = [&](int tile, float4 (&va)[8]) {
-            const int m0 = tile * kPx;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int blk = xw * 8 + e;
-                const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
-                const int m = m0 + px;
-                va[e] = (m < p.M && ch < p.kin) ? *reinterpret_cast<const float4 *>(p.Yprev + (size_t)m * p.ldp + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        const int ldp = p.ldp, kin = p.kin;
+        const bool raw = p.x_raw != 0;
+        // block e: pixel group e & 3, channel group 2*xw + (e >> 2)
+        const int chA = (xw * 2) * 16 + qd * 4, chB = chA + 16;
+        const float4 avA = *reinterpret_cast<const float4 *>(&sm.pa[chA]), bvA = *reinterpret_cast<const float4 *>(&sm.pb[chA]);
+        const float4 avB = *reinterpret_cast<const float4 *>(&sm.pa[chB]), bvB = *reinterpret_cast<const float4 *>(&sm.pb[chB]);
+        const bool okA = chA < kin, okB = chB < kin;
+        const float *x0 = p.Yprev + (size_t)r8 * ldp + chA;
+        const size_t tile_stride = (size_t)kPx * ldp;
+        const uint32_t xt_offA = (uint32_t)chA * 128u + (uint32_t)(r8 & 3) * 4u;      // chB: + 16*128; (chB & 4) == (chA & 4)
+        const uint32_t t0s = (uint32_t)((r8 >> 2) ^ (chA & 4)) << 4;
+
+        auto ldblk = [&](int tile, int e, float4 &xa) {
+            const bool ok = ((e < 4) ? okA : okB) && (tile * kPx + (e & 3) * 8 + r8 < M);
+            xa = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)tile * tile_stride + (size_t)((e & 3) * 8) * ldp + (e >> 2) * 16)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        auto process = [&](int tile, int s, int n, const float4 (&va)[8]) {
-            const int m0 = tile * kPx;
+        float4 va[8];
+        int s = 0, n = 0;
+        const int gstep = gridDim.x;
+        int tile = blockIdx.x;
+        if (tile < num_tiles) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ldblk(tile, e, va[e]);
+        }
+        for (; tile < num_tiles; tile += gstep) {
+            const int next = tile + gstep;
+            const bool has_next = next < num_tiles;
             warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
+            unsigned char *xt = sm.xt[s] + xt_offA;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int blk = xw * 8 + e;
-                const int px = (blk & 3) * 8 + r8, ch = (blk >> 2) * 16 + qd * 4;
                 float4 o = va[e];
-                if (!p.x_raw) {
-                    const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
+                if (has_next) ldblk(next, e, va[e]);
+                if (!raw) {
+                    const float4 av = (e < 4) ? avA : avB, bv = (e < 4) ? bvA : bvB;
                     o.x = softplus_log2(fmaf(o.x, av.x, bv.x)); o.y = softplus_log2(fmaf(o.y, av.y, bv.y));
                     o.z = softplus_log2(fmaf(o.z, av.z, bv.z)); o.w = softplus_log2(fmaf(o.w, av.w, bv.w));
                 }
-                if (m0 + px >= p.M) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tile * kPx + (e & 3) * 8 + r8 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
                 o = to_tf32(o);
-                unsigned char *tt = sm.xt[s] + (uint32_t)ch * 128u + (uint32_t)(px & 3) * 4u;
-                const uint32_t u0 = (uint32_t)((px >> 2) ^ (ch & 4));
-                *reinterpret_cast<float *>(tt + 0 * 128 + ((u0 ^ 0u) << 4)) = o.x;
-                *reinterpret_cast<float *>(tt + 1 * 128 + ((u0 ^ 1u) << 4)) = o.y;
-                *reinterpret_cast<float *>(tt + 2 * 128 + ((u0 ^ 2u) << 4)) = o.z;
-                *reinterpret_cast<float *>(tt + 3 * 128 + ((u0 ^ 3u) << 4)) = o.w;
+                unsigned char *tt = xt + (e >> 2) * (16 * 128);
+                *reinterpret_cast<float *>(tt + 0 * 128 + (t0s ^ (uint32_t)(((2 * (e & 3)) ^ 0) << 4))) = o.x;
+                *reinterpret_cast<float *>(tt + 1 * 128 + (t0s ^ (uint32_t)(((2 * (e & 3)) ^ 1) << 4))) = o.y;
+                *reinterpret_cast<float *>(tt + 2 * 128 + (t0s ^ (uint32_t)(((2 * (e & 3)) ^ 2) << 4))) = o.z;
+                *reinterpret_cast<float *>(tt + 3 * 128 + (t0s ^ (uint32_t)(((2 * (e & 3)) ^ 3) << 4))) = o.w;
             }
             fence_proxy_async_smem();
             warp_arrive(&sm.full[s], lane);
-        };
-        float4 a0[8], a1[8];
-        int s = 0, n = 0;
-        int tile = blockIdx.x;
-        if (tile < num_tiles) load(tile, a0);
-        while (tile < num_tiles) {
-            const int t1 = tile + gridDim.x;
-            if (t1 < num_tiles) load(t1, a1);
-            process(tile, s, n, a0);
             if (++s == kBStages) { s = 0; ++n; }
-            tile = t1;
-            if (tile >= num_tiles) break;
-            const int t2 = tile + gridDim.x;
-            if (t2 < num_tiles) load(t2, a0);
-            process(tile, s, n, a1);
-            if (++s == kBStages) { s = 0; ++n; }
-            tile = t2;
         }
     } else if (warp == kBwdMmaWarp) {
         // ================================ MMA issuer ================================
