@@ -10,6 +10,9 @@ import os
 
 from .build import LIB_PATH
 
+# developer override used by tools/variants.py to time / test experiment builds of the same library (same C ABI)
+LIB_PATH = os.environ.get("GA_LIB_PATH", LIB_PATH)
+
 c_f32p = ctypes.POINTER(ctypes.c_float)
 c_vp = ctypes.c_void_p
 

@@ -17,6 +17,21 @@
 #include "gemm.cuh"
 #include "tc_common.cuh"
 
+// timing-ablation switches for tools/variants.py (never set in the product build): 1 no global loads in the producers, 2 no activation
+// math, 4 no MMA issue, 8 no epilogue math, 16 no epilogue global traffic
+#ifndef GA_ABLATE
+#define GA_ABLATE 0
+#endif
+// GA_TC_TIMING=1: every warp of CTA 0 prints the cycles it spent inside mbarrier waits (tools/variants.py; never set in the product build)
+#ifndef GA_TC_TIMING
+#define GA_TC_TIMING 0
+#endif
+#if GA_TC_TIMING
+#define TWAIT(slot, call) do { const long long t0_ = clock64(); call; tw_[slot] += clock64() - t0_; } while (0)
+#else
+#define TWAIT(slot, call) call
+#endif
+
 namespace ga {
 namespace {
 
@@ -26,8 +41,17 @@ constexpr int kBM = 128, kBN = 128;
 constexpr int kChunkBytes = kBM * 128;          // one 32-channel chunk of a 128-row tile: 16 KB
 constexpr int kMaxChunks = 4;                    // K <= 128
 constexpr int kStageBytes = kMaxChunks * kChunkBytes;   // 64 KB
-constexpr int kTcThreads = 13 * 32;     // 8 producer warps, 1 MMA warp, 4 epilogue warps
-constexpr int kFwdMmaWarp = 8, kFwdEpiWarp0 = 9;
+#ifndef GA_FWD_PWARPS
+#define GA_FWD_PWARPS 8
+#endif
+constexpr int kFwdPWarps = GA_FWD_PWARPS;                 // producer warps (8 or 16)
+constexpr int kFwdRowsPerThread = 128 / kFwdPWarps;      // float4 loads per producer thread per tile
+#ifndef GA_FWD_EWARPS
+#define GA_FWD_EWARPS 8
+#endif
+constexpr int kFwdEWarps = GA_FWD_EWARPS;                 // epilogue warps (4, or 8: two per TMEM lane quarter, half the channels each)
+constexpr int kTcThreads = (kFwdPWarps + 1 + kFwdEWarps) * 32;
+constexpr int kFwdMmaWarp = kFwdPWarps, kFwdEpiWarp0 = kFwdPWarps + 1;
 constexpr uint32_t kTmemCols = 256;
 
 struct TcFwdParams {
@@ -59,11 +83,15 @@ tc_fwd_kernel(const TcFwdParams p)
     TcFwdSmem &sm = *reinterpret_cast<TcFwdSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int num_tiles = (p.M + kBM - 1) / kBM;
+#if GA_TC_TIMING
+    long long tw_[2] = {0, 0};
+    const long long tstart_ = clock64();
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm.full[s], 8); mbar_init(&sm.empty[s], 4);         // arrivals are per WARP (warp_arrive)
-            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 4);
+            mbar_init(&sm.full[s], kFwdPWarps * kArrivalsPerWarp); mbar_init(&sm.empty[s], kFwdEWarps * kArrivalsPerWarp);         // arrivals are per WARP (warp_arrive)
+            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], kFwdEWarps * kArrivalsPerWarp);
         }
         fence_barrier_init();
     }
@@ -87,51 +115,50 @@ tc_fwd_kernel(const TcFwdParams p)
     if (warp < kFwdMmaWarp) {
         // ================================ producers ================================
         // warp w owns channel chunk c = w & 3 (its BatchNorm coefficients live in registers) and row groups 2i + (w >> 2);
-        // one warp instruction = 4 rows x 128 B.  Rolling software pipeline: as soon as row group i of the current tile has been
-        // consumed, row group i of the NEXT tile is loaded into the same register, so 16 loads per thread stay in flight.
+        // one warp instruction = 4 rows x 128 B.  All 16 loads of a tile are in flight before the stage is even free (a rolling
+        // refill pipeline measured 20 % slower: its loads queue behind the transform of the previous tile).
         const int rl = lane >> 3, u = lane & 7;
         const int c = warp & 3, rg0 = warp >> 2;
         const int k = c * 32 + u * 4;
         const bool kin = k < p.K;
         float4 av = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kin) { av = *reinterpret_cast<const float4 *>(&sm.sa[k]); bv = *reinterpret_cast<const float4 *>(&sm.sb[k]); }
-        const bool act = p.a != nullptr;
+        const bool act = p.a != nullptr && !(GA_ABLATE & 2);
         {   // work in the log2 domain: z * log2(e) comes straight out of the FMA
             const float L2E = 1.44269504089f;
             av.x *= L2E; av.y *= L2E; av.z *= L2E; av.w *= L2E; bv.x *= L2E; bv.y *= L2E; bv.z *= L2E; bv.w *= L2E;
         }
         const int M = p.M, ldx = p.ldx;
-        const int r0 = rg0 * 4 + rl;                                 // row of group i: r0 + 8 i  ->  (r & 7) == (r0 & 7) for every i
+        constexpr int kRowStep = kFwdPWarps;                         // rows between a thread's consecutive loads (8 or 16)
+        const int r0 = rg0 * 4 + rl;                                 // row of group i: r0 + kRowStep i  ->  (r & 7) == (r0 & 7) for every i
         const float *x0 = p.X + (size_t)r0 * ldx + k;
         const size_t tile_stride = (size_t)kBM * ldx;
         const uint32_t soff = (uint32_t)c * kChunkBytes + sw128_offset(r0, u);      // + i * 8 * 128
         const bool chunk_used = c * 32 < p.K;
         auto ldrow = [&](int tile, int i, float4 &v) {
-            const bool ok = kin && (tile * kBM + r0 + 8 * i < M);
-            v = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)tile * tile_stride + (size_t)(8 * i) * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool ok = kin && (tile * kBM + r0 + kRowStep * i < M);
+            if (GA_ABLATE & 1) { v = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); return; }
+            v = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)tile * tile_stride + (size_t)(kRowStep * i) * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        float4 v[16];
         const int gstep = gridDim.x;
-        int tile = blockIdx.x;
-        if (tile < num_tiles) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) ldrow(tile, i, v[i]);
-        }
-        for (int it = 0; tile < num_tiles; tile += gstep, ++it) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gstep, ++it) {
             const int s = it & 1, n = it >> 1;
-            const int next = tile + gstep;
-            const bool has_next = next < num_tiles;
-            warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
-            unsigned char *dst = sm.a[s] + soff;
+            float4 v[kFwdRowsPerThread];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float4 x = v[i];
-                if (has_next) ldrow(next, i, v[i]);
-                if (act) {
-                    x.x = softplus_log2(fmaf(x.x, av.x, bv.x)); x.y = softplus_log2(fmaf(x.y, av.y, bv.y));
-                    x.z = softplus_log2(fmaf(x.z, av.z, bv.z)); x.w = softplus_log2(fmaf(x.w, av.w, bv.w));
+            for (int i = 0; i < kFwdRowsPerThread; ++i) ldrow(tile, i, v[i]);
+            TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
+            unsigned char *dst = sm.a[s] + soff;
+            if (chunk_used) {
+#pragma unroll
+                for (int i = 0; i < kFwdRowsPerThread; ++i) {
+                    float4 x = v[i];
+                    if (act) {
+                        x.x = softplus_log2(fmaf(x.x, av.x, bv.x)); x.y = softplus_log2(fmaf(x.y, av.y, bv.y));
+                        x.z = softplus_log2(fmaf(x.z, av.z, bv.z)); x.w = softplus_log2(fmaf(x.w, av.w, bv.w));
+                    }
+                    *reinterpret_cast<float4 *>(dst + i * (kRowStep * 128)) = to_tf32(x);
                 }
-                if (chunk_used) *reinterpret_cast<float4 *>(dst + i * 1024) = to_tf32(x);
             }
             fence_proxy_async_smem();
             warp_arrive(&sm.full[s], lane);
@@ -143,14 +170,14 @@ tc_fwd_kernel(const TcFwdParams p)
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1, n = it >> 1;
-            warp_wait(&sm.full[s], n & 1, lane);
-            warp_wait(&sm.tmem_empty[s], (n & 1) ^ 1, lane);
+            TWAIT(0, warp_wait(&sm.full[s], n & 1, lane));
+            TWAIT(1, warp_wait(&sm.tmem_empty[s], (n & 1) ^ 1, lane));
             tc_fence_after_sync();
             if (lane == 0) {
                 constexpr uint32_t hi = desc_hi(1024);
                 const uint32_t a_lo = desc_lo(smem_u32(sm.a[s]), 16), w_lo = desc_lo(w_addr, 16);
                 const uint32_t d = tmem_base + (uint32_t)s * kBN;
-                const int nk = p.K / 8;           // 16 (K = 128) or 9 (K = 72)
+                const int nk = (GA_ABLATE & 4) ? 0 : p.K / 8;           // 16 (K = 128) or 9 (K = 72)
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     if (k < nk) {
@@ -167,59 +194,83 @@ tc_fwd_kernel(const TcFwdParams p)
         // ================================ epilogue ================================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;               // tile row == TMEM lane
-        const int et = (warp - kFwdEpiWarp0) * 32 + lane;   // 0..127: channel owned for the statistics
-        double dsum = 0.0, dsq = 0.0;
+        constexpr int kRowsPerWarp = kBM / kFwdEWarps, kColBlocks = 32 / kFwdEWarps;      // store rows per warp; 16-column blocks staged per warp
+        constexpr int kEpiThreads = kFwdEWarps * 32;
+        const int wr = warp - kFwdEpiWarp0;          // rows [kRowsPerWarp wr, +kRowsPerWarp) of the tile are stored by this warp
+        const int half = wr >> 2;                    // which channel half this warp drains from TMEM (always 0 with 4 warps)
+        const float4 bias4 = *reinterpret_cast<const float4 *>(&sm.sbias[lane * 4]);      // the store phase owns channels 4 lane .. 4 lane + 3
+        double dsum[4] = {0.0, 0.0, 0.0, 0.0}, dsq[4] = {0.0, 0.0, 0.0, 0.0};
+        const bool accumulate = p.accumulate && !(GA_ABLATE & 16);
         int it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const int s = it & 1, n = it >> 1;
             const int m0 = tile * kBM;
-            warp_wait(&sm.mma_done[s], n & 1, lane);
+            TWAIT(0, warp_wait(&sm.mma_done[s], n & 1, lane));
             tc_fence_after_sync();
             unsigned char *stg = sm.a[s];            // the MMA has finished reading this stage: reuse it as staging
-#pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * kBN + cc * 32, v);
+#pragma unroll 2
+            for (int cb = 0; cb < kColBlocks; ++cb) {
+                const int cc = half * kColBlocks + cb;
+                float v[16];
+                tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * kBN + cc * 16, v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int un = cc * 8 + j;
-                    float4 o = make_float4(v[4 * j] + sm.sbias[un * 4], v[4 * j + 1] + sm.sbias[un * 4 + 1], v[4 * j + 2] + sm.sbias[un * 4 + 2],
-                                           v[4 * j + 3] + sm.sbias[un * 4 + 3]);
-                    *reinterpret_cast<float4 *>(stg + row * 512 + ((un ^ (row & 31)) << 4)) = o;
-                }
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4 *>(stg + row * 512 + (((cc * 4 + j) ^ (row & 31)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
             tc_fence_before_sync();
             warp_arrive(&sm.tmem_empty[s], lane);          // accumulator drained
-            named_bar_sync(1, 128);
-            // coalesced row stores (each warp: 32 rows, one 512-byte row per instruction)
-            const int wr = warp - kFwdEpiWarp0;
-            for (int r = wr * 32; r < wr * 32 + 32; ++r) {
-                const int m = m0 + r;
-                if (m >= p.M) break;
-                float4 *sp = reinterpret_cast<float4 *>(stg + r * 512 + ((lane ^ (r & 31)) << 4));
-                float4 o = *sp;
-                float4 *gp = reinterpret_cast<float4 *>(p.Y + (size_t)m * p.ldy + lane * 4);
-                if (p.accumulate) {
-                    const float4 e = *gp;
-                    o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
-                    *sp = o;
+            TWAIT(1, named_bar_sync(1, kEpiThreads));
+            // coalesced row stores (one 512-byte row per warp instruction) + bias + the BatchNorm statistics of this warp's rows
+            const int rows = p.M - m0 - wr * kRowsPerWarp;  // valid rows of this warp's slice (may be <= 0 or > kRowsPerWarp)
+            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = cs;
+            const unsigned char *sp0 = stg + (wr * kRowsPerWarp) * 512;
+            float *gp0 = p.Y + (size_t)(m0 + wr * kRowsPerWarp) * p.ldy + lane * 4;
+#pragma unroll 1
+            for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
+                float4 e[4];
+                if (accumulate) {              // the existing rows are fetched four at a time so that one memory latency covers them all
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        e[k] = (i0 + k < rows) ? *reinterpret_cast<const float4 *>(gp0 + (size_t)(i0 + k) * p.ldy) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                *gp = o;
-            }
-            if (p.sum) {
-                if (p.accumulate) named_bar_sync(1, 128);
-                float cs = 0.f, cq = 0.f;
-                const int rows = min(kBM, p.M - m0);
-                for (int r = 0; r < rows; ++r) {
-                    const float x = *reinterpret_cast<const float *>(stg + r * 512 + (((et >> 2) ^ (r & 31)) << 4) + (et & 3) * 4);
-                    cs += x; cq = fmaf(x, x, cq);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = i0 + k;
+                    if (i < rows) {
+                        float4 o = *reinterpret_cast<const float4 *>(sp0 + i * 512 + ((lane ^ ((wr * kRowsPerWarp + i) & 31)) << 4));
+                        o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+                        if (accumulate) { o.x += e[k].x; o.y += e[k].y; o.z += e[k].z; o.w += e[k].w; }
+                        if (!(GA_ABLATE & 16)) *reinterpret_cast<float4 *>(gp0 + (size_t)i * p.ldy) = o;
+                        if (!(GA_ABLATE & 8)) {
+                            cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
+                            cq.x = fmaf(o.x, o.x, cq.x); cq.y = fmaf(o.y, o.y, cq.y); cq.z = fmaf(o.z, o.z, cq.z); cq.w = fmaf(o.w, o.w, cq.w);
+                        }
+                    }
                 }
-                dsum += (double)cs; dsq += (double)cq;
             }
+            dsum[0] += (double)cs.x; dsum[1] += (double)cs.y; dsum[2] += (double)cs.z; dsum[3] += (double)cs.w;
+            dsq[0] += (double)cq.x; dsq[1] += (double)cq.y; dsq[2] += (double)cq.z; dsq[3] += (double)cq.w;
             warp_arrive(&sm.empty[s], lane);               // staging consumed: the producers may refill this stage
         }
-        if (p.sum) { atomicAdd(&p.sum[et], dsum); atomicAdd(&p.sumsq[et], dsq); }
+        if (p.sum) {
+            // combine the warps' partial sums through shared memory (stage 0 is idle by now): 2 atomics per channel per CTA
+            double *red = reinterpret_cast<double *>(sm.a[0]);
+            named_bar_sync(1, kEpiThreads);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { red[(wr * 8 + k) * 32 + lane] = dsum[k]; red[(wr * 8 + 4 + k) * 32 + lane] = dsq[k]; }
+            named_bar_sync(1, kEpiThreads);
+            if (wr < 4) {
+                const int et = wr * 32 + lane, l = et >> 2, k = et & 3;      // channel et = 4 l + k
+                double ts = 0.0, tq = 0.0;
+#pragma unroll
+                for (int w = 0; w < kFwdEWarps; ++w) { ts += red[(w * 8 + k) * 32 + l]; tq += red[(w * 8 + 4 + k) * 32 + l]; }
+                atomicAdd(&p.sum[et], ts); atomicAdd(&p.sumsq[et], tq);
+            }
+        }
     }
+#if GA_TC_TIMING
+    if (blockIdx.x == 0 && lane == 0) printf("TCT fwd K=%d warp %d total %lld wait0 %lld wait1 %lld tiles %d\n", p.K, warp, clock64() - tstart_, tw_[0], tw_[1], (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x);
+#endif
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kFwdMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
@@ -284,8 +335,12 @@ constexpr int kBStages = 3;
 constexpr int kGkChunk = kPx * 128;       // 4 KB: [32 px rows][32 channels]
 constexpr int kGkTile = 4 * kGkChunk;     // 16 KB
 constexpr int kTTile = 128 * 128;         // 16 KB: [128 channel rows][32 px]
-constexpr int kBwdThreads = 17 * 32;      // 8 G-producer warps, 4 X-producer warps, 1 MMA warp, 4 epilogue warps (96 regs/thread)
-constexpr int kBwdMmaWarp = 12, kBwdEpiWarp0 = 13;
+#ifndef GA_BWD_EWARPS
+#define GA_BWD_EWARPS 4
+#endif
+constexpr int kBwdEWarps = GA_BWD_EWARPS;  // epilogue warps: 4 (each 2 x 16 pixels) or 8 (two per TMEM lane quarter, 16 pixels each)
+constexpr int kBwdThreads = (17 + kBwdEWarps) * 32;      // 8 G-producer warps, 8 X-producer warps, 1 MMA warp, epilogue warps
+constexpr int kBwdMmaWarp = 16, kBwdEpiWarp0 = 17;
 constexpr uint32_t kBwdTmemCols = 256;    // [0,128): dW accumulator; 128 + 32 s: dX^T accumulator of stage s
 
 struct TcBwdParams {
@@ -321,11 +376,15 @@ tc_bwd_kernel(const TcBwdParams p)
     TcBwdSmem &sm = *reinterpret_cast<TcBwdSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int num_tiles = (p.M + kPx - 1) / kPx;
+#if GA_TC_TIMING
+    long long tw_[2] = {0, 0};
+    const long long tstart_ = clock64();
+#endif
 
     if (tid == 0) {
         for (int s = 0; s < kBStages; ++s) {
-            mbar_init(&sm.full[s], 12); mbar_init(&sm.empty[s], 4);        // arrivals are per WARP (warp_arrive)
-            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 4);
+            mbar_init(&sm.full[s], 16 * kArrivalsPerWarp); mbar_init(&sm.empty[s], kBwdEWarps * kArrivalsPerWarp);        // arrivals are per WARP (warp_arrive)
+            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], kBwdEWarps * kArrivalsPerWarp);
         }
         fence_barrier_init();
     }
@@ -390,6 +449,7 @@ tc_bwd_kernel(const TcBwdParams p)
             const float *pz = dz0 + (size_t)tile * tile_stride + (size_t)(e * 8) * ldg;
             const float *py = y0 + (size_t)tile * tile_stride + (size_t)(e * 8) * ldg;
             const bool ok = tile * kPx + e * 8 + r8 < M;
+            if (GA_ABLATE & 1) { za = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); ya = za; return; }
             za = ok ? *reinterpret_cast<const float4 *>(pz) : make_float4(0.f, 0.f, 0.f, 0.f);
             ya = ok ? *reinterpret_cast<const float4 *>(py) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
@@ -404,7 +464,7 @@ tc_bwd_kernel(const TcBwdParams p)
         for (; tile < num_tiles; tile += gstep) {
             const int next = tile + gstep;
             const bool has_next = next < num_tiles;
-            warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
+            TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
             unsigned char *gk = sm.gk[s] + gk_off, *gt = sm.gt[s] + gt_off;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -426,53 +486,49 @@ tc_bwd_kernel(const TcBwdParams p)
         }
     } else if (warp < kBwdMmaWarp) {
         const int r8 = lane & 7, qd = lane >> 3;
-        const int xw = warp - 8;
         const int ldp = p.ldp, kin = p.kin;
-        const bool raw = p.x_raw != 0;
-        // block e: pixel group e & 3, channel group 2*xw + (e >> 2)
-        const int chA = (xw * 2) * 16 + qd * 4, chB = chA + 16;
-        const float4 avA = *reinterpret_cast<const float4 *>(&sm.pa[chA]), bvA = *reinterpret_cast<const float4 *>(&sm.pb[chA]);
-        const float4 avB = *reinterpret_cast<const float4 *>(&sm.pa[chB]), bvB = *reinterpret_cast<const float4 *>(&sm.pb[chB]);
-        const bool okA = chA < kin, okB = chB < kin;
-        const float *x0 = p.Yprev + (size_t)r8 * ldp + chA;
+        const bool raw = p.x_raw != 0 || (GA_ABLATE & 2);
+        // X warp xw owns the 4 pixel groups of channel group xw (16 channels): block e is pixel group e
+        const int ch = (warp - 8) * 16 + qd * 4;
+        const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
+        const bool okc = ch < kin;
+        const float *x0 = p.Yprev + (size_t)r8 * ldp + ch;
         const size_t tile_stride = (size_t)kPx * ldp;
-        const uint32_t xt_offA = (uint32_t)chA * 128u + (uint32_t)(r8 & 3) * 4u;      // chB: + 16*128; (chB & 4) == (chA & 4)
-        const uint32_t t0s = (uint32_t)((r8 >> 2) ^ (chA & 4)) << 4;
+        const uint32_t xt_off = (uint32_t)ch * 128u + (uint32_t)(r8 & 3) * 4u;
+        const uint32_t t0s = (uint32_t)((r8 >> 2) ^ (ch & 4)) << 4;
 
         auto ldblk = [&](int tile, int e, float4 &xa) {
-            const bool ok = ((e < 4) ? okA : okB) && (tile * kPx + (e & 3) * 8 + r8 < M);
-            xa = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)tile * tile_stride + (size_t)((e & 3) * 8) * ldp + (e >> 2) * 16)
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool ok = okc && (tile * kPx + e * 8 + r8 < M);
+            if (GA_ABLATE & 1) { xa = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); return; }
+            xa = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)tile * tile_stride + (size_t)(e * 8) * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        float4 va[8];
+        float4 va[4];
         int s = 0, n = 0;
         const int gstep = gridDim.x;
         int tile = blockIdx.x;
         if (tile < num_tiles) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) ldblk(tile, e, va[e]);
+            for (int e = 0; e < 4; ++e) ldblk(tile, e, va[e]);
         }
         for (; tile < num_tiles; tile += gstep) {
             const int next = tile + gstep;
             const bool has_next = next < num_tiles;
-            warp_wait(&sm.empty[s], (n & 1) ^ 1, lane);
-            unsigned char *xt = sm.xt[s] + xt_offA;
+            TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
+            unsigned char *xt = sm.xt[s] + xt_off;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < 4; ++e) {
                 float4 o = va[e];
                 if (has_next) ldblk(next, e, va[e]);
                 if (!raw) {
-                    const float4 av = (e < 4) ? avA : avB, bv = (e < 4) ? bvA : bvB;
                     o.x = softplus_log2(fmaf(o.x, av.x, bv.x)); o.y = softplus_log2(fmaf(o.y, av.y, bv.y));
                     o.z = softplus_log2(fmaf(o.z, av.z, bv.z)); o.w = softplus_log2(fmaf(o.w, av.w, bv.w));
                 }
-                if (tile * kPx + (e & 3) * 8 + r8 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (tile * kPx + e * 8 + r8 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
                 o = to_tf32(o);
-                unsigned char *tt = xt + (e >> 2) * (16 * 128);
-                *reinterpret_cast<float *>(tt + 0 * 128 + (t0s ^ (uint32_t)(((2 * (e & 3)) ^ 0) << 4))) = o.x;
-                *reinterpret_cast<float *>(tt + 1 * 128 + (t0s ^ (uint32_t)(((2 * (e & 3)) ^ 1) << 4))) = o.y;
-                *reinterpret_cast<float *>(tt + 2 * 128 + (t0s ^ (uint32_t)(((2 * (e & 3)) ^ 2) << 4))) = o.z;
-                *reinterpret_cast<float *>(tt + 3 * 128 + (t0s ^ (uint32_t)(((2 * (e & 3)) ^ 3) << 4))) = o.w;
+                *reinterpret_cast<float *>(xt + 0 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 0) << 4))) = o.x;
+                *reinterpret_cast<float *>(xt + 1 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 1) << 4))) = o.y;
+                *reinterpret_cast<float *>(xt + 2 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 2) << 4))) = o.z;
+                *reinterpret_cast<float *>(xt + 3 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 3) << 4))) = o.w;
             }
             fence_proxy_async_smem();
             warp_arrive(&sm.full[s], lane);
@@ -485,10 +541,11 @@ tc_bwd_kernel(const TcBwdParams p)
         const uint32_t wt_addr = smem_u32(sm.wt);
         int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            warp_wait(&sm.full[s], n & 1, lane);
-            warp_wait(&sm.tmem_empty[s], (n & 1) ^ 1, lane);
+            TWAIT(0, warp_wait(&sm.full[s], n & 1, lane));
+            TWAIT(1, warp_wait(&sm.tmem_empty[s], (n & 1) ^ 1, lane));
             tc_fence_after_sync();
-            if (lane == 0) {
+            if (lane == 0 && (GA_ABLATE & 4)) mma_commit(&sm.mma_done[s]);
+            if (lane == 0 && !(GA_ABLATE & 4)) {
                 constexpr uint32_t hi = desc_hi(1024);
                 const uint32_t wt_lo = desc_lo(wt_addr, 16), gk_lo = desc_lo(smem_u32(sm.gk[s]), 16), gt_lo = desc_lo(smem_u32(sm.gt[s]), 16),
                                xt_lo = desc_lo(smem_u32(sm.xt[s]), 16);
@@ -511,65 +568,73 @@ tc_bwd_kernel(const TcBwdParams p)
         // ================================ epilogue: one input channel per thread ================================
         // 4 warps (TMEM lane quarter = warp & 3).  A thread's BatchNorm scalars are constants; sigmoid(z_{l-1}) and
         // xhat_{l-1} are recovered from x = softplus(z) in the X^T tile (no global re-read); 2 x 16 pixels per tile.
-        const int ew = warp - kBwdEpiWarp0;          // 0..3
+        const int ew = warp - kBwdEpiWarp0;          // 0..kBwdEWarps-1
+        constexpr int kPhStep = kBwdEWarps / 4, kStoreRows = kPx / kBwdEWarps;
         const int q = warp & 3;
         const int c = q * 32 + lane;                 // TMEM lane == input channel
-        const float cbeta = sm.pbeta[c], cinvg = sm.pinvg[c];
-        const bool final_mode = (p.mode == 0 || p.mode == 3);
-        const bool cvalid = c < p.kin;
+        // xhat = (z - beta) / gamma with z = x + ln2 * log2(sigmoid):  xhat = ln2/gamma * ls + (x / gamma - beta / gamma)
+        const float cinvg = sm.pinvg[c], cbg = sm.pbeta[c] * cinvg, cl2g = 0.69314718056f * cinvg;
+        const bool final_mode = (p.mode == 0 || p.mode == 3) && !(GA_ABLATE & 8);
+        const bool add_existing = p.mode >= 2 && c < p.kin && !(GA_ABLATE & 16);     // uniform per warp when kin is a multiple of 32
+        const uint32_t xrow = (uint32_t)c * 128u;
+        uint32_t xoff[8];                            // 16-byte unit of pixel quad u in this channel's X^T row (128-byte swizzle)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xoff[u] = xrow + (uint32_t)((u ^ (c & 7)) << 4);
+        const int ldo = p.ldo;
         double d1 = 0.0, d2 = 0.0;
         int s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = tile * kPx;
-            warp_wait(&sm.mma_done[s], n & 1, lane);
+            TWAIT(0, warp_wait(&sm.mma_done[s], n & 1, lane));
             tc_fence_after_sync();
-            float *stg = reinterpret_cast<float *>(sm.gk[s]);      // both products have consumed this stage: [32 px][128] staging
+            float *stg = reinterpret_cast<float *>(sm.gk[s]) + c;      // both products have consumed this stage: [32 px][128] staging
             float t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
-            for (int ph = 0; ph < 2; ++ph) {
-                float ev[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int m = m0 + ph * 16 + j;
-                    ev[j] = (p.mode >= 2 && cvalid && m < p.M) ? p.dZprev[(size_t)m * p.ldo + c] : 0.f;
-                }
+            for (int ph = ew >> 2; ph < 2; ph += kPhStep) {
                 float v[16];
                 tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx + ph * 16, v);
-                float xs[16];
+                if (add_existing) {
+                    // raw dX already accumulated by an earlier layer of this fan-in (rows >= M are never read: they contribute 0 below
+                    // because the producers zero G and X there)
+                    const float *ep = p.dZprev + (size_t)(m0 + ph * 16) * ldo + c;
+                    const int rows = p.M - (m0 + ph * 16);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += (j < rows) ? ep[(size_t)j * ldo] : 0.f;
+                }
                 if (final_mode) {
-                    const unsigned char *xr = sm.xt[s] + (uint32_t)c * 128u;
+                    const unsigned char *xr = sm.xt[s];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const float4 t = *reinterpret_cast<const float4 *>(xr + ((((ph * 4 + u) ^ (c & 7))) << 4));
-                        // the producers stored x + half a TF32 ulp (bit pattern + 0x1000, nothing truncated): undo it -> exact fp32 x
-                        xs[4 * u] = __uint_as_float(__float_as_uint(t.x) - 0x1000u); xs[4 * u + 1] = __uint_as_float(__float_as_uint(t.y) - 0x1000u);
-                        xs[4 * u + 2] = __uint_as_float(__float_as_uint(t.z) - 0x1000u); xs[4 * u + 3] = __uint_as_float(__float_as_uint(t.w) - 0x1000u);
+                        const float4 t = *reinterpret_cast<const float4 *>(xr + (ph ? xoff[4 + u] : xoff[u]));
+                        const float tx[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            // the producers stored x + half a TF32 ulp (bit pattern + 0x1000, nothing truncated): undo it -> exact fp32 x
+                            const float x = __uint_as_float(__float_as_uint(tx[k]) - 0x1000u);
+                            float em, ls;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(em) : "f"(-1.44269504089f * x));
+                            const float sg = 1.f - em;                                  // sigmoid(z) = 1 - exp(-softplus(z))
+                            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ls) : "f"(fmaxf(sg, 1e-30f)));
+                            const float dx = v[4 * u + k] * sg;                         // 0 for pixels >= M (G and X are zero there)
+                            v[4 * u + k] = dx;
+                            t1 += dx;
+                            t2 = fmaf(dx, fmaf(ls, cl2g, fmaf(x, cinvg, -cbg)), t2);
+                        }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float dx = v[j] + ev[j];
-                    if (final_mode) {
-                        float em, ls;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(em) : "f"(-1.44269504089f * xs[j]));
-                        const float sg = 1.f - em;
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ls) : "f"(fmaxf(sg, 1e-30f)));
-                        const float z = fmaf(0.69314718056f, ls, xs[j]);
-                        dx *= sg;
-                        if (m0 + ph * 16 + j < p.M) { t1 += dx; t2 = fmaf(dx, (z - cbeta) * cinvg, t2); }
-                    }
-                    stg[(ph * 16 + j) * 128 + c] = dx;
-                }
+                for (int j = 0; j < 16; ++j) stg[(ph * 16 + j) * 128] = v[j];
             }
             tc_fence_before_sync();
             warp_arrive(&sm.tmem_empty[s], lane);
             d1 += (double)t1; d2 += (double)t2;
-            named_bar_sync(1, 4 * 32);
-            for (int r = ew * 8; r < ew * 8 + 8; ++r) {
+            TWAIT(1, named_bar_sync(1, kBwdEWarps * 32));
+#pragma unroll
+            for (int r = ew * kStoreRows; r < ew * kStoreRows + kStoreRows; ++r) {
                 const int m = m0 + r;
                 if (m >= p.M) break;
-                if (lane * 4 < p.kin)
-                    *reinterpret_cast<float4 *>(p.dZprev + (size_t)m * p.ldo + lane * 4) = *reinterpret_cast<const float4 *>(stg + r * 128 + lane * 4);
+                if (lane * 4 < p.kin && !(GA_ABLATE & 16))
+                    *reinterpret_cast<float4 *>(p.dZprev + (size_t)m * p.ldo + lane * 4) = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(sm.gk[s]) + r * 128 + lane * 4);
             }
             warp_arrive(&sm.empty[s], lane);
             if (++s == kBStages) { s = 0; ++n; }
@@ -578,7 +643,7 @@ tc_bwd_kernel(const TcBwdParams p)
         // flush the weight-gradient accumulator: lane == output channel; every MMA was covered by the last mma_done wait
         tc_fence_after_sync();
 #pragma unroll 1
-        for (int cc = 0; cc < 8; ++cc) {
+        for (int cc = (ew >> 2) * (8 / kPhStep); cc < ((ew >> 2) + 1) * (8 / kPhStep); ++cc) {      // with 8 warps each pair splits the columns
             float v[16];
             tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 16, v);
 #pragma unroll
@@ -586,6 +651,9 @@ tc_bwd_kernel(const TcBwdParams p)
                 if (cc * 16 + j < p.kin) atomicAdd(p.dW + (size_t)c * p.lddw + cc * 16 + j, v[j]);
         }
     }
+#if GA_TC_TIMING
+    if (blockIdx.x == 0 && lane == 0) printf("TCT bwd mode=%d kin=%d warp %d total %lld wait0 %lld wait1 %lld tiles %d\n", p.mode, p.kin, warp, clock64() - tstart_, tw_[0], tw_[1], (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x);
+#endif
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kBwdMmaWarp) tmem_dealloc(tmem_base, kBwdTmemCols);

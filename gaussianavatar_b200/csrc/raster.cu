@@ -287,8 +287,33 @@ tile_ranges_kernel(int64_t R, const uint64_t *__restrict__ keys, uint2 *__restri
     if (k == R - 1) ranges[t].y = (uint32_t)R;
 }
 
-// K6: one CTA per 16x16 tile, one thread per pixel; the tile's depth-ordered list is staged through shared
-// memory 256 entries at a time.
+// Squared distance from a Gaussian's centre beyond which it is certain that the compositing loop skips it
+// (alpha = min(0.99, o exp(power)) < 1/255):  power <= -0.5 lmin |d|^2 with lmin the smaller eigenvalue of the conic.
+// Conservative by construction (1 % slack on alpha, lmin pushed down by its round-off, 0.1 % on the radius), so culling a
+// (Gaussian, sub-tile) pair never changes a result: every pair that could pass the exact per-pixel tests is still
+// evaluated with the exact arithmetic.  Returns -1 (always culled) for opacity below the threshold, +inf (never culled) for
+// an indefinite or NaN conic.
+__device__ __forceinline__ float cull_radius2(const float4 co)
+{
+    if (co.w <= 0.f) return -1.f;
+    const float thr = logf(255.f * co.w) + 0.01f;
+    if (thr <= 0.f) return -1.f;
+    const float mid = 0.5f * (co.x + co.z), hd = 0.5f * (co.x - co.z);
+    const float lmin = mid - sqrtf(hd * hd + co.y * co.y) - 1e-5f * fabsf(mid);
+    if (!(lmin > 0.f)) return INFINITY;
+    return 2.002f * thr / lmin;
+}
+
+// Squared distance from point c to the pixel rectangle [x0,x1] x [y0,y1] (0 inside).
+__device__ __forceinline__ float rect_dist2(const float2 c, float x0, float x1, float y0, float y1)
+{
+    const float ex = fmaxf(fmaxf(x0 - c.x, c.x - x1), 0.f), ey = fmaxf(fmaxf(y0 - c.y, c.y - y1), 0.f);
+    return ex * ex + ey * ey;
+}
+
+// K6: one CTA per 16x16 tile, one thread per pixel; the tile's depth-ordered list is staged through shared memory 256
+// entries at a time.  Each warp owns an 8x4-pixel sub-tile: 32 list entries are tested against the sub-tile in parallel
+// (one per lane, cull_radius2) and only the survivors are walked by the per-pixel loop, in list order.
 __global__ void __launch_bounds__(kBlock)
 render_fwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
                   const float2 *__restrict__ xy, const float4 *__restrict__ conic_o, const float *__restrict__ colors,
@@ -298,9 +323,13 @@ render_fwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
     __shared__ float2 s_xy[kBlock];
     __shared__ float4 s_co[kBlock];
     __shared__ float s_rgb[3][kBlock];
+    __shared__ float s_rc2[kBlock];
 
     const int tid = threadIdx.y * kTile + threadIdx.x;
-    const int px = blockIdx.x * kTile + threadIdx.x, py = blockIdx.y * kTile + threadIdx.y;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int sx = blockIdx.x * kTile + (warp & 1) * 8, sy = blockIdx.y * kTile + (warp >> 1) * 4;
+    const int px = sx + (lane & 7), py = sy + (lane >> 3);
+    const float x0f = (float)sx, x1f = (float)(sx + 7), y0f = (float)sy, y1f = (float)(sy + 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
@@ -309,36 +338,48 @@ render_fwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
 
     bool done = !inside;
     float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    uint32_t contributor = 0, last = 0;
+    uint32_t last = 0;
 
     for (int r = 0; r < rounds; ++r, todo -= kBlock) {
         if (__syncthreads_count(done) == kBlock) break;
         const int progress = r * kBlock + tid;
         if (range.x + progress < range.y) {
             const uint32_t g = point_list[range.x + progress];
+            const float4 co = conic_o[g];
             s_xy[tid] = xy[g];
-            s_co[tid] = conic_o[g];
+            s_co[tid] = co;
             s_rgb[0][tid] = colors[3 * (size_t)g];
             s_rgb[1][tid] = colors[3 * (size_t)g + 1];
             s_rgb[2][tid] = colors[3 * (size_t)g + 2];
+            s_rc2[tid] = cull_radius2(co);
         }
         __syncthreads();
         const int n = min(kBlock, todo);
-        for (int j = 0; !done && j < n; ++j) {
-            ++contributor;
-            const float2 c = s_xy[j];
-            const float dx = c.x - pxf, dy = c.y - pyf;
-            const float4 co = s_co[j];
-            const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-            if (power > 0.f) continue;
-            const float alpha = fminf(0.99f, co.w * expf(power));
-            if (alpha < 1.0f / 255.0f) continue;
-            const float test_T = T * (1.f - alpha);
-            if (test_T < 0.0001f) { done = true; continue; }
-            const float w = alpha * T;
-            C0 += s_rgb[0][j] * w; C1 += s_rgb[1][j] * w; C2 += s_rgb[2][j] * w;
-            T = test_T;
-            last = contributor;
+        if (__all_sync(0xffffffffu, done)) continue;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+            const int jt = j0 + lane;
+            bool hit = false;
+            if (jt < n) hit = !(rect_dist2(s_xy[jt], x0f, x1f, y0f, y1f) > s_rc2[jt]);
+            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            while (mask) {
+                const int j = j0 + __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (done) continue;
+                const float2 c = s_xy[j];
+                const float dx = c.x - pxf, dy = c.y - pyf;
+                const float4 co = s_co[j];
+                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                if (power > 0.f) continue;
+                const float alpha = fminf(0.99f, co.w * expf(power));
+                if (alpha < 1.0f / 255.0f) continue;
+                const float test_T = T * (1.f - alpha);
+                if (test_T < 0.0001f) { done = true; continue; }
+                const float w = alpha * T;
+                C0 += s_rgb[0][j] * w; C1 += s_rgb[1][j] * w; C2 += s_rgb[2][j] * w;
+                T = test_T;
+                last = (uint32_t)(r * kBlock + j + 1);
+            }
+            if (__all_sync(0xffffffffu, done)) break;
         }
     }
     if (inside) {
@@ -403,11 +444,14 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
     __shared__ float4 s_co[kBlock];
     __shared__ float s_rgb[3][kBlock];
     __shared__ float s_acc[9][kBlock];
+    __shared__ float s_rc2[kBlock];
     __shared__ uint32_t s_max[kBlock / 32];
 
     const int tid = threadIdx.y * kTile + threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const int px = blockIdx.x * kTile + threadIdx.x, py = blockIdx.y * kTile + threadIdx.y;
+    const int sx = blockIdx.x * kTile + (warp & 1) * 8, sy = blockIdx.y * kTile + (warp >> 1) * 4;      // 8x4 sub-tile per warp
+    const int px = sx + (lane & 7), py = sy + (lane >> 3);
+    const float x0f = (float)sx, x1f = (float)(sx + 7), y0f = (float)sy, y1f = (float)(sy + 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
@@ -445,16 +489,25 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
         const bool have = progress < todo;
         if (have) {
             const uint32_t g = point_list[range.x + todo - 1 - progress];
+            const float4 co = conic_o[g];
             s_id[tid] = g;
             s_xy[tid] = xy[g];
-            s_co[tid] = conic_o[g];
+            s_co[tid] = co;
             s_rgb[0][tid] = colors[3 * (size_t)g];
             s_rgb[1][tid] = colors[3 * (size_t)g + 1];
             s_rgb[2][tid] = colors[3 * (size_t)g + 2];
+            s_rc2[tid] = cull_radius2(co);
         }
         __syncthreads();
         const int n = (int)min((uint32_t)kBlock, todo - (uint32_t)r * kBlock);
-        for (int j = 0; j < n; ++j) {
+        for (int j0 = 0; j0 < n; j0 += 32) {
+          const int jt = j0 + lane;
+          bool hit = false;
+          if (jt < n) hit = !(rect_dist2(s_xy[jt], x0f, x1f, y0f, y1f) > s_rc2[jt]);
+          uint32_t mask = __ballot_sync(0xffffffffu, hit);
+          while (mask) {
+            const int j = j0 + __ffs(mask) - 1;
+            mask &= mask - 1;
             const uint32_t index = todo - 1 - ((uint32_t)r * kBlock + j);  // 0-based position in the tile list
             bool active = index < last_contributor;
             float2 c; float4 co; float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
@@ -503,6 +556,7 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
                 vo = warp_sum(vo);
                 if (lane == 0) atomicAdd(&s_acc[8][j], vo);
             }
+          }
         }
         __syncthreads();
         if (have) {

@@ -38,6 +38,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // Warp-granular handshakes: ONE lane polls / arrives, the rest of the warp parks on the warp barrier.  With per-thread
 // try_wait loops the ~500 waiting threads of a CTA flood the shared-memory pipe with barrier polls (7.4 M polls per launch in
 // the ncu profile) and every full/empty handoff is hundreds of serialised shared-memory atomics.
+#ifndef GA_TC_THREAD_SYNC
+#define GA_TC_THREAD_SYNC 0
+#endif
+#if GA_TC_THREAD_SYNC
+constexpr int kArrivalsPerWarp = 32;
+__device__ __forceinline__ void warp_wait(uint64_t *bar, uint32_t parity, int) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void warp_arrive(uint64_t *bar, int) { mbar_arrive(bar); }
+#else
+constexpr int kArrivalsPerWarp = 1;
 __device__ __forceinline__ void warp_wait(uint64_t *bar, uint32_t parity, int lane)
 {
     if (lane == 0) mbar_wait(bar, parity);
@@ -48,6 +57,7 @@ __device__ __forceinline__ void warp_arrive(uint64_t *bar, int lane)
     __syncwarp();
     if (lane == 0) mbar_arrive(bar);
 }
+#endif
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
