@@ -334,7 +334,7 @@ constexpr int kPx = 32;
 constexpr int kBStages = 3;
 constexpr int kGkChunk = kPx * 128;       // 4 KB: [32 px rows][32 channels]
 constexpr int kGkTile = 4 * kGkChunk;     // 16 KB
-constexpr int kTTile = 128 * 128;         // 16 KB: [128 channel rows][32 px]
+constexpr int kMnTile = 4 * kGkChunk;     // 16 KB: MN-major image [4 x 32-channel chunks][32 px][128 B] (32-byte-base swizzle)
 #ifndef GA_BWD_EWARPS
 #define GA_BWD_EWARPS 4
 #endif
@@ -361,8 +361,8 @@ struct TcBwdParams {
 struct alignas(1024) TcBwdSmem {
     unsigned char wt[4 * 128 * 128];                   // 64 KB: W^T, rows = input channel, K = output channel
     unsigned char gk[kBStages][kGkTile];               // G   rows = pixel,          K = output channel   (dgrad B operand)
-    unsigned char gt[kBStages][kTTile];                // G^T rows = output channel, K = pixel            (wgrad A operand)
-    unsigned char xt[kBStages][kTTile];                // X^T rows = input channel,  K = pixel            (wgrad B operand)
+    unsigned char gm[kBStages][kMnTile];               // G   MN-major: M = output channel, K = pixel     (wgrad A operand)
+    unsigned char xm[kBStages][kMnTile];               // X   MN-major: N = input channel,  K = pixel     (wgrad B operand)
     float gA[128], gB[128], gC[128];                   // dY = gA dZ + gB Y + gC  (BatchNorm backward folded to two FMAs)
     float pa[128], pb[128], pbeta[128], pinvg[128];    // layer l-1: z log2e = y pa + pb ; xhat = (z - pbeta) * pinvg
     uint64_t full[kBStages], empty[kBStages], mma_done[kBStages], tmem_empty[kBStages];
@@ -422,122 +422,107 @@ tc_bwd_kernel(const TcBwdParams p)
     tc_fence_after_sync();
     const uint32_t tmem_base = sm.tmem_base;
 
-    // ================================ producers: warps 0-7 build G (two layouts), warps 8-11 build X^T ==================
-    // The tile is 4 pixel groups (8 px) x 8 channel groups (16 ch) = 32 blocks of (8 px x 64 B).  A G warp owns the 4 pixel
-    // groups of ONE channel group (so its BatchNorm coefficients are thread constants), an X warp owns two channel groups.
-    // Loads are software-pipelined in registers (the NEXT tile's loads are issued before the current tile is transformed),
-    // and every global / shared offset is a thread constant plus a compile-time term: the loops below are almost pure
-    // LDG / FFMA / STS (the first version of this kernel spent 75% of its issue slots on address and predicate arithmetic).
+    // ================================ producers: warps 0-7 build G (two swizzles), warps 8-15 build X ==================
+    // Both wgrad operands are consumed MN-major (pixel = K index), which for 32-bit elements means the 128-byte swizzle with a
+    // 32-byte base (layout type 1; the physical layout was decoded with tools/exp_umma_probe.cu):
+    //     byte(px, c) = (c / 32) * LBO + (px / 4) * SBO + (px % 4) * 128 + ((((c % 32) / 8) ^ (px % 4)) * 32) + (c % 8) * 4
+    // so a pixel's 32 channels stay one permuted 128-byte row, exactly like the K-major image the dgrad needs (16-byte units
+    // XOR px % 8).  A warp instruction therefore covers 4 pixels x 128 B: full-line global loads, and every quarter-warp
+    // stores one whole row -> both images are written with conflict-free STS.128, no transposition anywhere.
+    // Warp w owns the 32-channel chunk j = w & 3 (its BatchNorm coefficients are thread constants) and pixel groups
+    // (w >> 2) + 2 e, e = 0..3.  Loads are software-pipelined (block e of the NEXT tile is fetched as soon as block e of the
+    // current one has been consumed) and every offset is a thread constant plus a compile-time term.
     const int M = p.M;
-    if (warp < 8) {
-        const int r8 = lane & 7, qd = lane >> 3;
-        const int ch = warp * 16 + qd * 4;                                   // this thread's 4 output channels (all tiles, all blocks)
-        const float4 cA = *reinterpret_cast<const float4 *>(&sm.gA[ch]), cB = *reinterpret_cast<const float4 *>(&sm.gB[ch]),
-                     cC = *reinterpret_cast<const float4 *>(&sm.gC[ch]);
-        const int ldg = p.ldg;
-        const bool has_y = p.ga != nullptr;
-        const float *dz0 = p.dZ + (size_t)r8 * ldg + ch, *y0 = (has_y ? p.Y : p.dZ) + (size_t)r8 * ldg + ch;   // block e adds e*8 rows
-        const size_t tile_stride = (size_t)kPx * ldg;
-        // shared offsets: block e is pixel px = e*8 + r8  ->  px & 7 == r8, px >> 2 == 2e + (r8 >> 2), px & 3 == r8 & 3
-        const uint32_t gk_off = (uint32_t)(ch >> 5) * kGkChunk + (uint32_t)r8 * 128u + (uint32_t)((((ch & 31) >> 2) ^ r8) << 4);   // + e*1024
-        const uint32_t gt_off = (uint32_t)ch * 128u + (uint32_t)(r8 & 3) * 4u;                                               // + i*128 + unit
-        const uint32_t t0s = (uint32_t)((r8 >> 2) ^ (ch & 4)) << 4;          // unit << 4 = t0s ^ ((2e ^ i) << 4)
-
-        // Rolling software pipeline: as soon as block e of the current tile has been consumed, block e of the NEXT tile is
-        // loaded into the same registers, so a tile's worth of loads is always in flight with a single register set.
-        auto ldblk = [&](int tile, int e, float4 &za, float4 &ya) {
-            const float *pz = dz0 + (size_t)tile * tile_stride + (size_t)(e * 8) * ldg;
-            const float *py = y0 + (size_t)tile * tile_stride + (size_t)(e * 8) * ldg;
-            const bool ok = tile * kPx + e * 8 + r8 < M;
-            if (GA_ABLATE & 1) { za = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); ya = za; return; }
-            za = ok ? *reinterpret_cast<const float4 *>(pz) : make_float4(0.f, 0.f, 0.f, 0.f);
-            ya = ok ? *reinterpret_cast<const float4 *>(py) : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        float4 va[4], vb[4];
+    if (warp < kBwdMmaWarp) {
+        const int c16 = lane & 7, pxl = lane >> 3;
+        const int pw = warp & 7;
+        const int j = pw & 3, p0 = (pw >> 2) * 4 + pxl;                      // block e is pixel p0 + 8 e:  px & 7 == p0, px & 3 == pxl
+        const int ch = j * 32 + c16 * 4;                                     // this thread's 4 channels (all tiles, all blocks)
+        const uint32_t k_off = (uint32_t)j * kGkChunk + (uint32_t)p0 * 128u + (uint32_t)((c16 ^ p0) << 4);                       // + e * 1024
+        const uint32_t mn_off = (uint32_t)j * kGkChunk + (uint32_t)p0 * 128u + (uint32_t)((((c16 >> 1) ^ pxl) << 5) | ((c16 & 1) << 4));
         int s = 0, n = 0;
         const int gstep = gridDim.x;
         int tile = blockIdx.x;
-        if (tile < num_tiles) {
+        if (warp < 8) {
+            const float4 cA = *reinterpret_cast<const float4 *>(&sm.gA[ch]), cB = *reinterpret_cast<const float4 *>(&sm.gB[ch]),
+                         cC = *reinterpret_cast<const float4 *>(&sm.gC[ch]);
+            const int ldg = p.ldg;
+            const bool has_y = p.ga != nullptr;
+            const float *dz0 = p.dZ + (size_t)p0 * ldg + ch, *y0 = (has_y ? p.Y : p.dZ) + (size_t)p0 * ldg + ch;   // block e adds 8 e rows
+            const size_t tile_stride = (size_t)kPx * ldg;
+            auto ldblk = [&](int t, int e, float4 &za, float4 &ya) {
+                const bool ok = t * kPx + e * 8 + p0 < M;
+                if (GA_ABLATE & 1) { za = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); ya = za; return; }
+                za = ok ? *reinterpret_cast<const float4 *>(dz0 + (size_t)t * tile_stride + (size_t)(e * 8) * ldg) : make_float4(0.f, 0.f, 0.f, 0.f);
+                ya = ok ? *reinterpret_cast<const float4 *>(y0 + (size_t)t * tile_stride + (size_t)(e * 8) * ldg) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            float4 va[4], vb[4];
+            if (tile < num_tiles) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) ldblk(tile, e, va[e], vb[e]);
-        }
-        for (; tile < num_tiles; tile += gstep) {
-            const int next = tile + gstep;
-            const bool has_next = next < num_tiles;
-            TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
-            unsigned char *gk = sm.gk[s] + gk_off, *gt = sm.gt[s] + gt_off;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float4 o;
-                o.x = fmaf(cA.x, va[e].x, fmaf(cB.x, vb[e].x, cC.x)); o.y = fmaf(cA.y, va[e].y, fmaf(cB.y, vb[e].y, cC.y));
-                o.z = fmaf(cA.z, va[e].z, fmaf(cB.z, vb[e].z, cC.z)); o.w = fmaf(cA.w, va[e].w, fmaf(cB.w, vb[e].w, cC.w));
-                if (tile * kPx + e * 8 + r8 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (has_next) ldblk(next, e, va[e], vb[e]);
-                o = to_tf32(o);
-                *reinterpret_cast<float4 *>(gk + e * 1024) = o;
-                *reinterpret_cast<float *>(gt + 0 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 0) << 4))) = o.x;
-                *reinterpret_cast<float *>(gt + 1 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 1) << 4))) = o.y;
-                *reinterpret_cast<float *>(gt + 2 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 2) << 4))) = o.z;
-                *reinterpret_cast<float *>(gt + 3 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 3) << 4))) = o.w;
+                for (int e = 0; e < 4; ++e) ldblk(tile, e, va[e], vb[e]);
             }
-            fence_proxy_async_smem();
-            warp_arrive(&sm.full[s], lane);
-            if (++s == kBStages) { s = 0; ++n; }
-        }
-    } else if (warp < kBwdMmaWarp) {
-        const int r8 = lane & 7, qd = lane >> 3;
-        const int ldp = p.ldp, kin = p.kin;
-        const bool raw = p.x_raw != 0 || (GA_ABLATE & 2);
-        // X warp xw owns the 4 pixel groups of channel group xw (16 channels): block e is pixel group e
-        const int ch = (warp - 8) * 16 + qd * 4;
-        const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
-        const bool okc = ch < kin;
-        const float *x0 = p.Yprev + (size_t)r8 * ldp + ch;
-        const size_t tile_stride = (size_t)kPx * ldp;
-        const uint32_t xt_off = (uint32_t)ch * 128u + (uint32_t)(r8 & 3) * 4u;
-        const uint32_t t0s = (uint32_t)((r8 >> 2) ^ (ch & 4)) << 4;
-
-        auto ldblk = [&](int tile, int e, float4 &xa) {
-            const bool ok = okc && (tile * kPx + e * 8 + r8 < M);
-            if (GA_ABLATE & 1) { xa = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); return; }
-            xa = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)tile * tile_stride + (size_t)(e * 8) * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
-        };
-        float4 va[4];
-        int s = 0, n = 0;
-        const int gstep = gridDim.x;
-        int tile = blockIdx.x;
-        if (tile < num_tiles) {
+            for (; tile < num_tiles; tile += gstep) {
+                const int next = tile + gstep;
+                const bool has_next = next < num_tiles;
+                TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
+                unsigned char *gk = sm.gk[s] + k_off, *gm = sm.gm[s] + mn_off;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) ldblk(tile, e, va[e]);
-        }
-        for (; tile < num_tiles; tile += gstep) {
-            const int next = tile + gstep;
-            const bool has_next = next < num_tiles;
-            TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
-            unsigned char *xt = sm.xt[s] + xt_off;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float4 o = va[e];
-                if (has_next) ldblk(next, e, va[e]);
-                if (!raw) {
-                    o.x = softplus_log2(fmaf(o.x, av.x, bv.x)); o.y = softplus_log2(fmaf(o.y, av.y, bv.y));
-                    o.z = softplus_log2(fmaf(o.z, av.z, bv.z)); o.w = softplus_log2(fmaf(o.w, av.w, bv.w));
+                for (int e = 0; e < 4; ++e) {
+                    float4 o;
+                    o.x = fmaf(cA.x, va[e].x, fmaf(cB.x, vb[e].x, cC.x)); o.y = fmaf(cA.y, va[e].y, fmaf(cB.y, vb[e].y, cC.y));
+                    o.z = fmaf(cA.z, va[e].z, fmaf(cB.z, vb[e].z, cC.z)); o.w = fmaf(cA.w, va[e].w, fmaf(cB.w, vb[e].w, cC.w));
+                    if (tile * kPx + e * 8 + p0 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_next) ldblk(next, e, va[e], vb[e]);
+                    o = to_tf32(o);
+                    *reinterpret_cast<float4 *>(gk + e * 1024) = o;
+                    *reinterpret_cast<float4 *>(gm + e * 1024) = o;
                 }
-                if (tile * kPx + e * 8 + r8 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                o = to_tf32(o);
-                *reinterpret_cast<float *>(xt + 0 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 0) << 4))) = o.x;
-                *reinterpret_cast<float *>(xt + 1 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 1) << 4))) = o.y;
-                *reinterpret_cast<float *>(xt + 2 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 2) << 4))) = o.z;
-                *reinterpret_cast<float *>(xt + 3 * 128 + (t0s ^ (uint32_t)(((2 * e) ^ 3) << 4))) = o.w;
+                fence_proxy_async_smem();
+                warp_arrive(&sm.full[s], lane);
+                if (++s == kBStages) { s = 0; ++n; }
             }
-            fence_proxy_async_smem();
-            warp_arrive(&sm.full[s], lane);
-            if (++s == kBStages) { s = 0; ++n; }
+        } else {
+            const int ldp = p.ldp;
+            const bool raw = p.x_raw != 0 || (GA_ABLATE & 2);
+            const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
+            const bool okc = ch < p.kin;
+            const float *x0 = p.Yprev + (size_t)p0 * ldp + ch;
+            const size_t tile_stride = (size_t)kPx * ldp;
+            auto ldblk = [&](int t, int e, float4 &xa) {
+                const bool ok = okc && (t * kPx + e * 8 + p0 < M);
+                if (GA_ABLATE & 1) { xa = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); return; }
+                xa = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)t * tile_stride + (size_t)(e * 8) * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            float4 va[4];
+            if (tile < num_tiles) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ldblk(tile, e, va[e]);
+            }
+            for (; tile < num_tiles; tile += gstep) {
+                const int next = tile + gstep;
+                const bool has_next = next < num_tiles;
+                TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
+                unsigned char *xm = sm.xm[s] + mn_off;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float4 o = va[e];
+                    if (has_next) ldblk(next, e, va[e]);
+                    if (!raw) {
+                        o.x = softplus_log2(fmaf(o.x, av.x, bv.x)); o.y = softplus_log2(fmaf(o.y, av.y, bv.y));
+                        o.z = softplus_log2(fmaf(o.z, av.z, bv.z)); o.w = softplus_log2(fmaf(o.w, av.w, bv.w));
+                    }
+                    if (!okc || tile * kPx + e * 8 + p0 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4 *>(xm + e * 1024) = to_tf32(o);
+                }
+                fence_proxy_async_smem();
+                warp_arrive(&sm.full[s], lane);
+                if (++s == kBStages) { s = 0; ++n; }
+            }
         }
     } else if (warp == kBwdMmaWarp) {
         // ================================ MMA issuer ================================
         constexpr uint32_t idesc_dgrad = make_idesc_tf32(128, kPx, false, false);
-        constexpr uint32_t idesc_wgrad = make_idesc_tf32(128, 128, false, false);
+        constexpr uint32_t idesc_wgrad = make_idesc_tf32(128, 128, true, true);      // both operands MN-major (K = pixel)
         const uint32_t wt_addr = smem_u32(sm.wt);
         int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -547,8 +532,10 @@ tc_bwd_kernel(const TcBwdParams p)
             if (lane == 0 && (GA_ABLATE & 4)) mma_commit(&sm.mma_done[s]);
             if (lane == 0 && !(GA_ABLATE & 4)) {
                 constexpr uint32_t hi = desc_hi(1024);
-                const uint32_t wt_lo = desc_lo(wt_addr, 16), gk_lo = desc_lo(smem_u32(sm.gk[s]), 16), gt_lo = desc_lo(smem_u32(sm.gt[s]), 16),
-                               xt_lo = desc_lo(smem_u32(sm.xt[s]), 16);
+                // MN-major images: 32-channel chunks kGkChunk apart (LBO), 4-pixel swizzle atoms 512 B apart (SBO), layout type 1
+                constexpr uint32_t hi_mn = (512u >> 4) | (1u << 14) | (1u << 29);
+                const uint32_t wt_lo = desc_lo(wt_addr, 16), gk_lo = desc_lo(smem_u32(sm.gk[s]), 16), gm_lo = desc_lo(smem_u32(sm.gm[s]), kGkChunk),
+                               xm_lo = desc_lo(smem_u32(sm.xm[s]), kGkChunk);
                 const uint32_t d_dx = tmem_base + 128 + (uint32_t)s * kPx;
                 // dX^T[in, px] = sum_out W^T[in, out] G[px, out]: 16 steps of 8 output channels
 #pragma unroll
@@ -558,7 +545,7 @@ tc_bwd_kernel(const TcBwdParams p)
                 // dW[out, in] += sum_px G^T[out, px] X^T[in, px]: 4 steps of 8 pixels
 #pragma unroll
                 for (int j = 0; j < kPx / 8; ++j)
-                    mma_tf32_lohi(tmem_base, gt_lo + (uint32_t)j * 2u, xt_lo + (uint32_t)j * 2u, hi, idesc_wgrad, (it > 0) || (j > 0));
+                    mma_tf32_lohi(tmem_base, gm_lo + (uint32_t)j * (1024u >> 4), xm_lo + (uint32_t)j * (1024u >> 4), hi_mn, idesc_wgrad, (it > 0) || (j > 0));
                 mma_commit(&sm.mma_done[s]);
             }
             __syncwarp();
@@ -576,10 +563,9 @@ tc_bwd_kernel(const TcBwdParams p)
         const float cinvg = sm.pinvg[c], cbg = sm.pbeta[c] * cinvg, cl2g = 0.69314718056f * cinvg;
         const bool final_mode = (p.mode == 0 || p.mode == 3) && !(GA_ABLATE & 8);
         const bool add_existing = p.mode >= 2 && c < p.kin && !(GA_ABLATE & 16);     // uniform per warp when kin is a multiple of 32
-        const uint32_t xrow = (uint32_t)c * 128u;
-        uint32_t xoff[8];                            // 16-byte unit of pixel quad u in this channel's X^T row (128-byte swizzle)
+        uint32_t xoff[4];                            // this channel's word inside the row of a pixel with px % 4 == i (MN-major image of X)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) xoff[u] = xrow + (uint32_t)((u ^ (c & 7)) << 4);
+        for (int i = 0; i < 4; ++i) xoff[i] = (uint32_t)(c >> 5) * kGkChunk + (uint32_t)((((lane >> 3) ^ i) << 5) + (lane & 7) * 4);
         const int ldo = p.ldo;
         double d1 = 0.0, d2 = 0.0;
         int s = 0, n = 0;
@@ -602,24 +588,19 @@ tc_bwd_kernel(const TcBwdParams p)
                     for (int j = 0; j < 16; ++j) v[j] += (j < rows) ? ep[(size_t)j * ldo] : 0.f;
                 }
                 if (final_mode) {
-                    const unsigned char *xr = sm.xt[s];
+                    const unsigned char *xr = sm.xm[s] + ph * (16 * 128);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float4 t = *reinterpret_cast<const float4 *>(xr + (ph ? xoff[4 + u] : xoff[u]));
-                        const float tx[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            // the producers stored x + half a TF32 ulp (bit pattern + 0x1000, nothing truncated): undo it -> exact fp32 x
-                            const float x = __uint_as_float(__float_as_uint(tx[k]) - 0x1000u);
-                            float em, ls;
-                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(em) : "f"(-1.44269504089f * x));
-                            const float sg = 1.f - em;                                  // sigmoid(z) = 1 - exp(-softplus(z))
-                            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ls) : "f"(fmaxf(sg, 1e-30f)));
-                            const float dx = v[4 * u + k] * sg;                         // 0 for pixels >= M (G and X are zero there)
-                            v[4 * u + k] = dx;
-                            t1 += dx;
-                            t2 = fmaf(dx, fmaf(ls, cl2g, fmaf(x, cinvg, -cbg)), t2);
-                        }
+                    for (int j = 0; j < 16; ++j) {
+                        // the producers stored x + half a TF32 ulp (bit pattern + 0x1000, nothing truncated): undo it -> exact fp32 x
+                        const float x = __uint_as_float(*reinterpret_cast<const uint32_t *>(xr + j * 128 + xoff[j & 3]) - 0x1000u);
+                        float em, ls;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(em) : "f"(-1.44269504089f * x));
+                        const float sg = 1.f - em;                                  // sigmoid(z) = 1 - exp(-softplus(z))
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ls) : "f"(fmaxf(sg, 1e-30f)));
+                        const float dx = v[j] * sg;                                 // 0 for pixels >= M (G and X are zero there)
+                        v[j] = dx;
+                        t1 += dx;
+                        t2 = fmaf(dx, fmaf(ls, cl2g, fmaf(x, cinvg, -cbg)), t2);
                     }
                 }
 #pragma unroll
