@@ -571,6 +571,16 @@ tc_bwd_kernel(const TcBwdParams p)
         int s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = tile * kPx;
+            // raw dX already accumulated by an earlier layer of this fan-in: fetched BEFORE waiting for the tensor core, and the second
+            // half while the first is being processed, so the latency hides behind the MMA and the sigmoid math (rows >= M are never read)
+            float ev[16];
+            auto ldev = [&](int ph) {
+                const float *ep = p.dZprev + (size_t)(m0 + ph * 16) * ldo + c;
+                const int rows = p.M - (m0 + ph * 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ev[j] = (j < rows) ? ep[(size_t)j * ldo] : 0.f;
+            };
+            if (add_existing) ldev(ew >> 2);
             TWAIT(0, warp_wait(&sm.mma_done[s], n & 1, lane));
             tc_fence_after_sync();
             float *stg = reinterpret_cast<float *>(sm.gk[s]) + c;      // both products have consumed this stage: [32 px][128] staging
@@ -580,12 +590,9 @@ tc_bwd_kernel(const TcBwdParams p)
                 float v[16];
                 tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx + ph * 16, v);
                 if (add_existing) {
-                    // raw dX already accumulated by an earlier layer of this fan-in (rows >= M are never read: they contribute 0 below
-                    // because the producers zero G and X there)
-                    const float *ep = p.dZprev + (size_t)(m0 + ph * 16) * ldo + c;
-                    const int rows = p.M - (m0 + ph * 16);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += (j < rows) ? ep[(size_t)j * ldo] : 0.f;
+                    for (int j = 0; j < 16; ++j) v[j] += ev[j];
+                    if (ph + kPhStep < 2) ldev(ph + kPhStep);
                 }
                 if (final_mode) {
                     const unsigned char *xr = sm.xm[s] + ph * (16 * 128);
