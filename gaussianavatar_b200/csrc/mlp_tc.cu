@@ -44,8 +44,9 @@ constexpr int kStageBytes = kMaxChunks * kChunkBytes;   // 64 KB
 #ifndef GA_FWD_PWARPS
 #define GA_FWD_PWARPS 8
 #endif
-constexpr int kFwdPWarps = GA_FWD_PWARPS;                 // producer warps (8 or 16)
-constexpr int kFwdRowsPerThread = 128 / kFwdPWarps;      // float4 loads per producer thread per tile
+constexpr int kFwdPWarps = GA_FWD_PWARPS;                 // producer warps: 8, or 16 = two groups of 8 that take alternate tiles (group g owns stage g)
+constexpr int kFwdGroups = kFwdPWarps / 8;
+constexpr int kFwdRowsPerThread = 16;                    // float4 loads per producer thread per tile
 #ifndef GA_FWD_EWARPS
 #define GA_FWD_EWARPS 8
 #endif
@@ -90,7 +91,7 @@ tc_fwd_kernel(const TcFwdParams p)
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm.full[s], kFwdPWarps * kArrivalsPerWarp); mbar_init(&sm.empty[s], kFwdEWarps * kArrivalsPerWarp);         // arrivals are per WARP (warp_arrive)
+            mbar_init(&sm.full[s], 8 * kArrivalsPerWarp); mbar_init(&sm.empty[s], kFwdEWarps * kArrivalsPerWarp);         // arrivals are per WARP (warp_arrive)
             mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], kFwdEWarps * kArrivalsPerWarp);
         }
         fence_barrier_init();
@@ -118,7 +119,8 @@ tc_fwd_kernel(const TcFwdParams p)
         // one warp instruction = 4 rows x 128 B.  All 16 loads of a tile are in flight before the stage is even free (a rolling
         // refill pipeline measured 20 % slower: its loads queue behind the transform of the previous tile).
         const int rl = lane >> 3, u = lane & 7;
-        const int c = warp & 3, rg0 = warp >> 2;
+        const int pw = warp & 7, grp = warp >> 3;
+        const int c = pw & 3, rg0 = pw >> 2;
         const int k = c * 32 + u * 4;
         const bool kin = k < p.K;
         float4 av = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -129,7 +131,7 @@ tc_fwd_kernel(const TcFwdParams p)
             av.x *= L2E; av.y *= L2E; av.z *= L2E; av.w *= L2E; bv.x *= L2E; bv.y *= L2E; bv.z *= L2E; bv.w *= L2E;
         }
         const int M = p.M, ldx = p.ldx;
-        constexpr int kRowStep = kFwdPWarps;                         // rows between a thread's consecutive loads (8 or 16)
+        constexpr int kRowStep = 8;                                  // rows between a thread's consecutive loads
         const int r0 = rg0 * 4 + rl;                                 // row of group i: r0 + kRowStep i  ->  (r & 7) == (r0 & 7) for every i
         const float *x0 = p.X + (size_t)r0 * ldx + k;
         const size_t tile_stride = (size_t)kBM * ldx;
@@ -141,8 +143,7 @@ tc_fwd_kernel(const TcFwdParams p)
             v = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)tile * tile_stride + (size_t)(kRowStep * i) * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         const int gstep = gridDim.x;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gstep, ++it) {
+        for (int it = grp, tile = blockIdx.x + grp * gstep; tile < num_tiles; tile += gstep * kFwdGroups, it += kFwdGroups) {
             const int s = it & 1, n = it >> 1;
             float4 v[kFwdRowsPerThread];
 #pragma unroll
@@ -635,8 +636,8 @@ tc_bwd_kernel(const TcBwdParams p)
             float v[16];
             tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + cc * 16, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (cc * 16 + j < p.kin) atomicAdd(p.dW + (size_t)c * p.lddw + cc * 16 + j, v[j]);
+            for (int g = 0; g < 4; ++g)          // kin and lddw are multiples of 4: 16-byte vector reductions
+                if (cc * 16 + g * 4 < p.kin) red_add_v4(p.dW + (size_t)c * p.lddw + cc * 16 + g * 4, v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
         }
     }
 #if GA_TC_TIMING
@@ -655,6 +656,7 @@ int launch_tc_bwd(const float *dZ, const float *Y, int ldg, const float *ga, con
 {
     GA_REQUIRE(kin % 4 == 0 && kin >= 4 && kin <= 128 && (!x_raw || mode == 1 || mode == 2), "tcgen05 backward: bad kin / mode");
     GA_REQUIRE(ldg % 4 == 0 && ldp % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0, "tcgen05 backward: leading dimensions must be multiples of 4");
+    GA_REQUIRE(lddw % 4 == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0, "tcgen05 backward: dW must be 16-byte aligned with lddw a multiple of 4");
     static bool attr_set = false;
     if (!attr_set) {
         GA_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcBwdSmem) + 1024));

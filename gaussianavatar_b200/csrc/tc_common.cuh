@@ -29,11 +29,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"      // %2: suspend-time hint -> the poll parks in hardware
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 // Warp-granular handshakes: ONE lane polls / arrives, the rest of the warp parks on the warp barrier.  With per-thread
 // try_wait loops the ~500 waiting threads of a CTA flood the shared-memory pipe with barrier polls (7.4 M polls per launch in
@@ -60,6 +60,12 @@ __device__ __forceinline__ void warp_arrive(uint64_t *bar, int lane)
 #endif
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 16-byte vector reduction to global memory (sm_90+): one L2 atomic for four consecutive floats
+__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 // ---- tensor memory ---------------------------------------------------------------------------------------------------
 // One full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *dst_smem.
