@@ -21,6 +21,8 @@ int launch_tc_bwd(const float *dZ, const float *Y, int ldg, const float *ga, con
                   float *dW, int lddw, float *dZprev, int ldo, int mode, double *s1, double *s2, int M, int kin, int x_raw, cudaStream_t st);
 int launch_tc_fwd(const float *X, int ldx, int K, const float *a, const float *b, const float *W, int ldw, const float *bias, float *Y,
                   int ldy, int accumulate, double *sum, double *sumsq, int M, cudaStream_t st);
+int launch_conv_tc(int mode, const float *in, const float *w, float *out, int Hf, int round_out, cudaStream_t st);
+int launch_round_tf32(const float *in, float *out, size_t n, cudaStream_t st);
 namespace {
 
 constexpr int kCg = 64;        // c_geom
@@ -57,7 +59,8 @@ Layout make_layout()
 }
 
 struct Workspace {
-    float *F[4];          // NHWC [Hf*Wf, 64]: geo, conv1, conv2, conv3
+    float *F[4];          // NHWC [Hf*Wf, 64]: geo, conv1, conv2, conv3 (tensor-core path: F[0..2] hold TF32-rounded values)
+    float *wr;            // [3][25*64*64] TF32-rounded copy of the conv weights (tensor-core path)
     float *dF[2];         // ping-pong gradients of the above
     float *feat;          // [M, 72]
     float *d_feat;        // [M, 72]
@@ -77,6 +80,7 @@ Workspace carve_ws(void *buf, int S, int Hf)
     const size_t M = (size_t)S * S, P = (size_t)Hf * Hf;
     for (int i = 0; i < 4; ++i) w.F[i] = c.take<float>(P * kCg);
     for (int i = 0; i < 2; ++i) w.dF[i] = c.take<float>(P * kCg);
+    w.wr = c.take<float>((size_t)3 * 25 * kCg * kCg);
     w.feat = c.take<float>(M * kFeatLd);
     w.d_feat = c.take<float>(M * kFeatLd);
     for (int i = 0; i < 5; ++i) w.Y[i] = c.take<float>(M * kH);
@@ -516,11 +520,21 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
         chw_to_hwc_kernel<<<cdiv(P, 64), 256, 0, st>>>(geo_nchw, w.F[0], P);
     }
     GA_CHECK_LAUNCH("chw_to_hwc_kernel");
-    for (int i = 0; i < 3; ++i) {
-        ALoadIm2colK<128> A{w.F[i], Hf, +1, P};
-        BLoadDirect<64> B{params + L.gconv[i], kCg, kCg, 25 * kCg};
-        EpiStoreStats E{w.F[i + 1], kCg, P, kCg, nullptr, nullptr, nullptr, false};
-        if (int rc = launch_gemm<128, 64>("geom_conv_fwd", A, B, E, P, kCg, 25 * kCg, 1, st)) return rc;
+    if (d->flags & GA_DECODER_TENSOR_CORES) {
+        // tcgen05 implicit GEMMs on TF32-rounded operands (what cuDNN computes for the reference's Conv2d): round the input and the
+        // weights once; every conv but the last writes its output already rounded (it is only ever read as an MMA operand again)
+        if (int rc = launch_round_tf32(w.F[0], w.F[0], (size_t)P * kCg, st)) return rc;
+        for (int i = 0; i < 3; ++i)
+            if (int rc = launch_round_tf32(params + L.gconv[i], w.wr + (size_t)i * 25 * kCg * kCg, (size_t)25 * kCg * kCg, st)) return rc;
+        for (int i = 0; i < 3; ++i)
+            if (int rc = launch_conv_tc(0, w.F[i], w.wr + (size_t)i * 25 * kCg * kCg, w.F[i + 1], Hf, i < 2, st)) return rc;
+    } else {
+        for (int i = 0; i < 3; ++i) {
+            ALoadIm2colK<128> A{w.F[i], Hf, +1, P};
+            BLoadDirect<64> B{params + L.gconv[i], kCg, kCg, 25 * kCg};
+            EpiStoreStats E{w.F[i + 1], kCg, P, kCg, nullptr, nullptr, nullptr, false};
+            if (int rc = launch_gemm<128, 64>("geom_conv_fwd", A, B, E, P, kCg, 25 * kCg, 1, st)) return rc;
+        }
     }
     {
         ProfScope _ps("sample_feat_fwd_kernel", st);
@@ -794,6 +808,16 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
     }
     GA_CHECK_LAUNCH("sample_feat_bwd_kernel");
     float *dcur = w.dF[0], *dnxt = w.dF[1];
+    if (d->flags & GA_DECODER_TENSOR_CORES) {
+        // the forward pass left F[0..2] and the weight copy TF32-rounded; the up-sampling gradient is rounded in place (it only
+        // feeds MMAs), every data gradient but the last is written rounded
+        if (int rc = launch_round_tf32(dcur, dcur, (size_t)P * kCg, st)) return rc;
+        for (int i = 2; i >= 0; --i) {
+            if (int rc = launch_conv_tc(2, w.F[i], dcur, d_params + L.gconv[i], Hf, 0, st)) return rc;
+            if (int rc = launch_conv_tc(1, dcur, w.wr + (size_t)i * 25 * kCg * kCg, dnxt, Hf, i > 0, st)) return rc;
+            float *t = dcur; dcur = dnxt; dnxt = t;
+        }
+    } else
     for (int i = 2; i >= 0; --i) {
         {
             ALoadIm2colD<128> A{w.F[i], Hf, 25 * kCg, P};

@@ -196,6 +196,15 @@ int ga_tc_linear_backward(int32_t M, const float *dZ, const float *Y, int32_t ld
                           const float *prev_coef, const float *W, int32_t ldw, float *dW, int32_t lddw, float *dZprev, int32_t ldo,
                           int32_t mode, double *s1, double *s2, void *stream);
 
+/* One 5x5, 64->64 channel, padding-2 convolution of the geometry net (model/modules.py:122-137; network.py:26,57) on the
+ * tensor cores (building block of ga_decoder_forward/backward, exposed for unit tests).  Feature maps are NHWC [Hf*Hf][64],
+ * weights [25 taps][64 ci][64 co]; operands must already hold TF32-representable values (ga_round_tf32).
+ * mode 0: out = conv(in, w); mode 1: out = data gradient for in = dL/dY; mode 2: out (dW, same layout as w) += weight gradient
+ * for in = X and w = dL/dY.  round_out != 0 rounds the result to TF32 (modes 0, 1). */
+int ga_tc_conv5x5(int32_t mode, int32_t Hf, const float *in, const float *w, float *out, int32_t round_out, void *stream);
+/* out[i] = in[i] rounded to TF32 (nearest, ties away; low 13 mantissa bits cleared).  n % 4 == 0; in-place allowed. */
+int ga_round_tf32(const float *in, float *out, int64_t n, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -147,3 +147,42 @@ def test_decoder_tf32_backward_vs_reference_fixture(name):
     assert max(worst.values()) < 3e-2, worst
     gg = geo.grad.cpu().numpy()
     assert abs(np.linalg.norm(gg) - float(d["geo_grad_norm"])) / float(d["geo_grad_norm"]) < 2e-2
+
+
+@pytest.mark.parametrize("Hf", [16, 40, 128])
+def test_tc_conv5x5_all_modes(Hf):
+    """tcgen05 implicit-GEMM 5x5 conv (forward, data gradient, weight gradient) vs fp64 torch conv2d on the same TF32-rounded
+    operands: only the accumulation order differs, so the tolerance is fp32 round-off (rel 1e-5)."""
+    import torch.nn.functional as F
+    from gaussianavatar_b200 import _lib
+    from gaussianavatar_b200._lib import ptr
+    g = torch.Generator().manual_seed(Hf)
+    P = Hf * Hf
+    x = torch.randn(P, 64, generator=g).to(DEV)
+    dy = torch.randn(P, 64, generator=g).to(DEV)
+    w = (torch.randn(25, 64, 64, generator=g) * 0.05).to(DEV)                 # [tap][ci][co]
+    st = torch.cuda.current_stream().cuda_stream
+    L = _lib.lib()
+    xr, dyr, wr = torch.empty_like(x), torch.empty_like(dy), torch.empty_like(w)
+    for src, dst in ((x, xr), (dy, dyr), (w, wr)):
+        _lib.check(L.ga_round_tf32(ptr(src), ptr(dst), src.numel(), st), "ga_round_tf32")
+    assert torch.equal(xr, tf32_trunc(x)) and torch.equal(wr, tf32_trunc(w))
+    y = torch.empty(P, 64, device=DEV); dx = torch.empty(P, 64, device=DEV); dw = torch.zeros(25, 64, 64, device=DEV)
+    _lib.check(L.ga_tc_conv5x5(0, Hf, ptr(xr), ptr(wr), ptr(y), 0, st), "conv fwd")
+    _lib.check(L.ga_tc_conv5x5(1, Hf, ptr(dyr), ptr(wr), ptr(dx), 0, st), "conv dgrad")
+    _lib.check(L.ga_tc_conv5x5(2, Hf, ptr(xr), ptr(dyr), ptr(dw), 0, st), "conv wgrad")
+    torch.cuda.synchronize()
+    # fp64 reference through autograd on the rounded operands
+    xn = xr.double().view(Hf, Hf, 64).permute(2, 0, 1)[None].requires_grad_(True)            # NCHW
+    wn = wr.double().view(5, 5, 64, 64).permute(3, 2, 0, 1).contiguous().requires_grad_(True)   # [co][ci][ky][kx]
+    yn = F.conv2d(xn, wn, padding=2)
+    yn.backward(dyr.double().view(Hf, Hf, 64).permute(2, 0, 1)[None])
+    rel = lambda a, b: ((a.double() - b).norm() / b.norm()).item()
+    assert rel(y, yn[0].permute(1, 2, 0).reshape(P, 64)) < 1e-5
+    assert rel(dx, xn.grad[0].permute(1, 2, 0).reshape(P, 64)) < 1e-5
+    assert rel(dw, wn.grad.permute(2, 3, 1, 0).reshape(25, 64, 64)) < 1e-5
+    # round_out stores the TF32-rounded result
+    y2 = torch.empty_like(y)
+    _lib.check(L.ga_tc_conv5x5(0, Hf, ptr(xr), ptr(wr), ptr(y2), 1, st), "conv fwd rounded")
+    torch.cuda.synchronize()
+    assert torch.equal(y2, tf32_trunc(y))
