@@ -25,6 +25,10 @@ int launch_conv_tc(int mode, const float *in, const float *w, float *out, int Hf
 int launch_round_tf32(const float *in, float *out, size_t n, cudaStream_t st);
 namespace {
 
+#ifndef GA_HEADS_CTAS_PER_SM
+#define GA_HEADS_CTAS_PER_SM 2
+#endif
+constexpr int kHeadsGrid = GA_HEADS_CTAS_PER_SM * kNumSMs;   // grid-stride CTAs of the heads kernels (2 per SM measured best: 4/6/8 lose to the per-CTA weight-gradient flush)
 constexpr int kCg = 64;        // c_geom
 constexpr int kH = 128;        // hsize
 constexpr int kFeatLd = 72;    // 64 sampled + 2 uv + 6 zero pad (multiple of 8)
@@ -179,7 +183,7 @@ sample_feat_fwd_kernel(int S, int Hf, const float *__restrict__ F, float *__rest
     }
 }
 
-// transpose of the above: scatter d_feat[m, 0:64] into dF (pre-zeroed) with float atomics
+// transpose of the above: scatter d_feat[m, 0:64] into dF (pre-zeroed) with 16-byte vector reductions
 __global__ void __launch_bounds__(256)
 sample_feat_bwd_kernel(int S, int Hf, const float *__restrict__ d_feat, float *__restrict__ dF)
 {
@@ -190,8 +194,7 @@ sample_feat_bwd_kernel(int S, int Hf, const float *__restrict__ d_feat, float *_
     const int i = (int)(m / S), j = (int)(m % S);
     const float4 g = *reinterpret_cast<const float4 *>(d_feat + m * kFeatLd + q * 4);
     if (Hf == S) {
-        float *p = dF + m * kCg + q * 4;
-        atomicAdd(p, g.x); atomicAdd(p + 1, g.y); atomicAdd(p + 2, g.z); atomicAdd(p + 3, g.w);
+        red_add_v4(dF + m * kCg + q * 4, g.x, g.y, g.z, g.w);
         return;
     }
     const Taps t = make_taps(i, j, S, Hf);
@@ -202,8 +205,7 @@ sample_feat_bwd_kernel(int S, int Hf, const float *__restrict__ d_feat, float *_
             const int x = t.x0 + dx, y = t.y0 + dy;
             if (x < 0 || x >= Hf || y < 0 || y >= Hf) continue;
             const float w = (dx ? t.wx1 : 1.f - t.wx1) * (dy ? t.wy1 : 1.f - t.wy1);
-            float *p = dF + ((size_t)y * Hf + x) * kCg + q * 4;
-            atomicAdd(p, w * g.x); atomicAdd(p + 1, w * g.y); atomicAdd(p + 2, w * g.z); atomicAdd(p + 3, w * g.w);
+            red_add_v4(dF + ((size_t)y * Hf + x) * kCg + q * 4, w * g.x, w * g.y, w * g.z, w * g.w);
         }
 }
 
@@ -619,9 +621,9 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
     {
         ProfScope _ps("heads_fwd_kernel", st);
         if (d->flags & GA_DECODER_TENSOR_CORES)
-            heads_fwd_kernel<true><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
+            heads_fwd_kernel<true><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
         else
-            heads_fwd_kernel<false><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
+            heads_fwd_kernel<false><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
     }
     GA_CHECK_LAUNCH("heads_fwd_kernel");
     return GA_OK;
@@ -662,30 +664,30 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         {
             ProfScope _ps("heads_bwd_kernel<0>", st);
             if (d->flags & GA_DECODER_TENSOR_CORES)
-                heads_bwd_kernel<0, true><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                heads_bwd_kernel<0, true><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                    dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
             else
-                heads_bwd_kernel<0, false><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                heads_bwd_kernel<0, false><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                     dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
         }
         GA_CHECK_LAUNCH("heads_bwd_kernel<0>");
         {
             ProfScope _ps("heads_bwd_kernel<1>", st);
             if (d->flags & GA_DECODER_TENSOR_CORES)
-                heads_bwd_kernel<1, true><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                heads_bwd_kernel<1, true><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                    dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
             else
-                heads_bwd_kernel<1, false><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                heads_bwd_kernel<1, false><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                     dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
         }
         GA_CHECK_LAUNCH("heads_bwd_kernel<1>");
         {
             ProfScope _ps("heads_bwd_kernel<2>", st);
             if (d->flags & GA_DECODER_TENSOR_CORES)
-                heads_bwd_kernel<2, true><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                heads_bwd_kernel<2, true><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                    dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
             else
-                heads_bwd_kernel<2, false><<<2 * kNumSMs, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                heads_bwd_kernel<2, false><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                     dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
         }
         GA_CHECK_LAUNCH("heads_bwd_kernel<2>");

@@ -567,12 +567,11 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
             if (a[0] != 0.f) atomicAdd(&d_colors[3 * (size_t)g], a[0]);
             if (a[1] != 0.f) atomicAdd(&d_colors[3 * (size_t)g + 1], a[1]);
             if (a[2] != 0.f) atomicAdd(&d_colors[3 * (size_t)g + 2], a[2]);
-            if (a[3] != 0.f) atomicAdd(&d_mean2D[g].x, a[3]);
-            if (a[4] != 0.f) atomicAdd(&d_mean2D[g].y, a[4]);
-            if (a[5] != 0.f) atomicAdd(&d_conic_op[g].x, a[5]);
-            if (a[6] != 0.f) atomicAdd(&d_conic_op[g].y, a[6]);
-            if (a[7] != 0.f) atomicAdd(&d_conic_op[g].z, a[7]);
-            if (kOpacity && a[8] != 0.f) atomicAdd(&d_conic_op[g].w, a[8]);
+            // 8- and 16-byte vector reductions (sm_90+): one L2 atomic per float2 / float4 instead of one per component
+            if (a[3] != 0.f || a[4] != 0.f)
+                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(&d_mean2D[g]), "f"(a[3]), "f"(a[4]) : "memory");
+            if (a[5] != 0.f || a[6] != 0.f || a[7] != 0.f || (kOpacity && a[8] != 0.f))
+                red_add_v4(&d_conic_op[g].x, a[5], a[6], a[7], kOpacity ? a[8] : 0.f);
         }
     }
 }

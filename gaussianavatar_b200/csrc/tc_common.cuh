@@ -61,12 +61,6 @@ __device__ __forceinline__ void warp_arrive(uint64_t *bar, int lane)
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// 16-byte vector reduction to global memory (sm_90+): one L2 atomic for four consecutive floats
-__device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)
-{
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 // ---- tensor memory ---------------------------------------------------------------------------------------------------
 // One full warp allocates `ncols` (power of two >= 32) columns; the base address lands in *dst_smem.
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols)

@@ -19,7 +19,7 @@ def build(specs):
         objs = []
         for o in base_objs:
             stem = os.path.basename(o)[:-2]
-            if stem in ("mlp_tc", "raster"):
+            if stem in ("mlp_tc", "raster", "decoder", "conv_tc"):
                 vo = os.path.join(VDIR, f"{stem}_{name}.o")
                 subprocess.run([nvcc, *B.NVCC_FLAGS, *flags, "-c", os.path.join(B._CSRC, stem + ".cu"), "-o", vo], check=True)
                 objs.append(vo)
@@ -47,7 +47,7 @@ for _ in range(2): step()
 torch.cuda.synchronize(); L.profile(True)
 for _ in range({iters}): step()
 rep = L.profile_report()
-print({os.path.basename(path)!r}, " ".join(f"{{k}}={{v[1]/{iters}:.3f}}ms/{{v[0]//{iters}}}" for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1]) if k.startswith("mlp_tc")))
+print({os.path.basename(path)!r}, " ".join(f"{{k}}={{v[1]/{iters}:.3f}}ms/{{v[0]//{iters}}}" for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1]) if k.startswith(("mlp_tc", "heads", "geom_conv", "sample_feat"))))
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     print(r.stdout.strip() or ("FAILED " + os.path.basename(path) + "\n" + r.stderr[-800:]))
