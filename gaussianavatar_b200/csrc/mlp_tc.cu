@@ -337,7 +337,7 @@ constexpr int kGkChunk = kPx * 128;       // 4 KB: [32 px rows][32 channels]
 constexpr int kGkTile = 4 * kGkChunk;     // 16 KB
 constexpr int kMnTile = 4 * kGkChunk;     // 16 KB: MN-major image [4 x 32-channel chunks][32 px][128 B] (32-byte-base swizzle)
 #ifndef GA_BWD_EWARPS
-#define GA_BWD_EWARPS 4
+#define GA_BWD_EWARPS 8
 #endif
 constexpr int kBwdEWarps = GA_BWD_EWARPS;  // epilogue warps: 4 (each 2 x 16 pixels) or 8 (two per TMEM lane quarter, 16 pixels each)
 constexpr int kBwdThreads = (17 + kBwdEWarps) * 32;      // 8 G-producer warps, 8 X-producer warps, 1 MMA warp, epilogue warps
