@@ -320,10 +320,12 @@ render_fwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
                   const float *__restrict__ bg, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
                   float *__restrict__ out)
 {
-    __shared__ float2 s_xy[kBlock];
-    __shared__ float4 s_co[kBlock];
-    __shared__ float s_rgb[3][kBlock];
-    __shared__ float s_rc2[kBlock];
+    // two staging buffers: the next 256 entries are fetched into registers while the current ones are composited and stored
+    // before the round's single barrier, so the gather latency hides behind the compositing
+    __shared__ float2 s_xy[2][kBlock];
+    __shared__ float4 s_co[2][kBlock];
+    __shared__ float s_rgb[2][3][kBlock];
+    __shared__ float s_rc2[2][kBlock];
 
     const int tid = threadIdx.y * kTile + threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -340,47 +342,58 @@ render_fwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
     float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     uint32_t last = 0;
 
+    // entry of this thread in the batch being fetched
+    float2 f_xy = make_float2(0.f, 0.f); float4 f_co = make_float4(0.f, 0.f, 0.f, 0.f); float f_r = 0.f, f_g = 0.f, f_b = 0.f;
+    auto fetch = [&](int r) {
+        const uint32_t i = range.x + (uint32_t)r * kBlock + tid;
+        if (i < range.y) {
+            const uint32_t g = point_list[i];
+            f_xy = xy[g]; f_co = conic_o[g];
+            f_r = colors[3 * (size_t)g]; f_g = colors[3 * (size_t)g + 1]; f_b = colors[3 * (size_t)g + 2];
+        }
+    };
+    auto stage = [&](int b) {
+        s_xy[b][tid] = f_xy; s_co[b][tid] = f_co;
+        s_rgb[b][0][tid] = f_r; s_rgb[b][1][tid] = f_g; s_rgb[b][2][tid] = f_b;
+        s_rc2[b][tid] = cull_radius2(f_co);
+    };
+    if (rounds > 0) { fetch(0); stage(0); }
+    __syncthreads();
+
     for (int r = 0; r < rounds; ++r, todo -= kBlock) {
-        if (__syncthreads_count(done) == kBlock) break;
-        const int progress = r * kBlock + tid;
-        if (range.x + progress < range.y) {
-            const uint32_t g = point_list[range.x + progress];
-            const float4 co = conic_o[g];
-            s_xy[tid] = xy[g];
-            s_co[tid] = co;
-            s_rgb[0][tid] = colors[3 * (size_t)g];
-            s_rgb[1][tid] = colors[3 * (size_t)g + 1];
-            s_rgb[2][tid] = colors[3 * (size_t)g + 2];
-            s_rc2[tid] = cull_radius2(co);
-        }
-        __syncthreads();
+        const int b = r & 1;
+        const bool more = r + 1 < rounds;
+        if (more) fetch(r + 1);
         const int n = min(kBlock, todo);
-        if (__all_sync(0xffffffffu, done)) continue;
-        for (int j0 = 0; j0 < n; j0 += 32) {
-            const int jt = j0 + lane;
-            bool hit = false;
-            if (jt < n) hit = !(rect_dist2(s_xy[jt], x0f, x1f, y0f, y1f) > s_rc2[jt]);
-            uint32_t mask = __ballot_sync(0xffffffffu, hit);
-            while (mask) {
-                const int j = j0 + __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (done) continue;
-                const float2 c = s_xy[j];
-                const float dx = c.x - pxf, dy = c.y - pyf;
-                const float4 co = s_co[j];
-                const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                if (power > 0.f) continue;
-                const float alpha = fminf(0.99f, co.w * expf(power));
-                if (alpha < 1.0f / 255.0f) continue;
-                const float test_T = T * (1.f - alpha);
-                if (test_T < 0.0001f) { done = true; continue; }
-                const float w = alpha * T;
-                C0 += s_rgb[0][j] * w; C1 += s_rgb[1][j] * w; C2 += s_rgb[2][j] * w;
-                T = test_T;
-                last = (uint32_t)(r * kBlock + j + 1);
+        if (!__all_sync(0xffffffffu, done)) {
+            for (int j0 = 0; j0 < n; j0 += 32) {
+                const int jt = j0 + lane;
+                bool hit = false;
+                if (jt < n) hit = !(rect_dist2(s_xy[b][jt], x0f, x1f, y0f, y1f) > s_rc2[b][jt]);
+                uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                while (mask) {
+                    const int j = j0 + __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (done) continue;
+                    const float2 c = s_xy[b][j];
+                    const float dx = c.x - pxf, dy = c.y - pyf;
+                    const float4 co = s_co[b][j];
+                    const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+                    if (power > 0.f) continue;
+                    const float alpha = fminf(0.99f, co.w * expf(power));
+                    if (alpha < 1.0f / 255.0f) continue;
+                    const float test_T = T * (1.f - alpha);
+                    if (test_T < 0.0001f) { done = true; continue; }
+                    const float w = alpha * T;
+                    C0 += s_rgb[b][0][j] * w; C1 += s_rgb[b][1][j] * w; C2 += s_rgb[b][2][j] * w;
+                    T = test_T;
+                    last = (uint32_t)(r * kBlock + j + 1);
+                }
+                if (__all_sync(0xffffffffu, done)) break;
             }
-            if (__all_sync(0xffffffffu, done)) break;
         }
+        if (more) stage(b ^ 1);          // buffer b^1 was last read in round r-1: every warp has passed that round's barrier
+        if (__syncthreads_count(done) == kBlock) break;
     }
     if (inside) {
         const size_t pid = (size_t)py * W + px, HW = (size_t)H * W;
@@ -431,20 +444,25 @@ __device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane)
 // components GaussianAvatar consumes), then across the CTA's eight warps in shared memory, so each (tile, Gaussian) pair
 // issues at most one global atomic per component.  kOpacity adds dL/dopacity (API completeness; the avatar's opacity is
 // a constant without gradient, model/avatar_model.py:80).
+#ifndef GA_RENDER_BWD_MINB
+#define GA_RENDER_BWD_MINB 1
+#endif
 template <bool kOpacity>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, GA_RENDER_BWD_MINB)
 render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
                   const float *__restrict__ bg, const float2 *__restrict__ xy, const float4 *__restrict__ conic_o,
                   const float *__restrict__ colors, const float *__restrict__ final_T,
                   const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dout,
                   float2 *__restrict__ d_mean2D, float4 *__restrict__ d_conic_op, float *__restrict__ d_colors)
 {
-    __shared__ uint32_t s_id[kBlock];
-    __shared__ float2 s_xy[kBlock];
-    __shared__ float4 s_co[kBlock];
-    __shared__ float s_rgb[3][kBlock];
-    __shared__ float s_acc[9][kBlock];
-    __shared__ float s_rc2[kBlock];
+    // staging and accumulators are double-buffered: round r composites buffer r & 1 while the entries of round r + 1 sit in
+    // registers (stored before the round's single barrier) and the previous round's accumulators are flushed after it
+    __shared__ uint32_t s_id[2][kBlock];
+    __shared__ float2 s_xy[2][kBlock];
+    __shared__ float4 s_co[2][kBlock];
+    __shared__ float s_rgb[2][3][kBlock];
+    __shared__ float s_acc[2][9][kBlock];
+    __shared__ float s_rc2[2][kBlock];
     __shared__ uint32_t s_max[kBlock / 32];
 
     const int tid = threadIdx.y * kTile + threadIdx.x;
@@ -470,7 +488,7 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
     for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) s_max[warp] = m;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) s_acc[k][tid] = 0.f;
+    for (int k = 0; k < 9; ++k) { s_acc[0][k][tid] = 0.f; s_acc[1][k][tid] = 0.f; }
     __syncthreads();
     uint32_t todo = 0;
 #pragma unroll
@@ -483,27 +501,33 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
     const int rounds = (int)((todo + kBlock - 1) / kBlock);
     const int vidx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // component this lane ends up owning
 
-    for (int r = 0; r < rounds; ++r) {
-        __syncthreads();
+    uint32_t f_id = 0; float2 f_xy = make_float2(0.f, 0.f); float4 f_co = make_float4(0.f, 0.f, 0.f, 0.f); float f_r = 0.f, f_g = 0.f, f_b = 0.f;
+    auto fetch = [&](int r) {
         const uint32_t progress = (uint32_t)r * kBlock + tid;
-        const bool have = progress < todo;
-        if (have) {
-            const uint32_t g = point_list[range.x + todo - 1 - progress];
-            const float4 co = conic_o[g];
-            s_id[tid] = g;
-            s_xy[tid] = xy[g];
-            s_co[tid] = co;
-            s_rgb[0][tid] = colors[3 * (size_t)g];
-            s_rgb[1][tid] = colors[3 * (size_t)g + 1];
-            s_rgb[2][tid] = colors[3 * (size_t)g + 2];
-            s_rc2[tid] = cull_radius2(co);
+        if (progress < todo) {
+            f_id = point_list[range.x + todo - 1 - progress];
+            f_xy = xy[f_id]; f_co = conic_o[f_id];
+            f_r = colors[3 * (size_t)f_id]; f_g = colors[3 * (size_t)f_id + 1]; f_b = colors[3 * (size_t)f_id + 2];
         }
-        __syncthreads();
+    };
+    auto stage = [&](int b) {
+        s_id[b][tid] = f_id; s_xy[b][tid] = f_xy; s_co[b][tid] = f_co;
+        s_rgb[b][0][tid] = f_r; s_rgb[b][1][tid] = f_g; s_rgb[b][2][tid] = f_b;
+        s_rc2[b][tid] = cull_radius2(f_co);
+    };
+    fetch(0); stage(0);
+    __syncthreads();
+
+    for (int r = 0; r < rounds; ++r) {
+        const int b = r & 1;
+        const bool more = r + 1 < rounds;
+        const bool have = (uint32_t)r * kBlock + tid < todo;
+        if (more) fetch(r + 1);
         const int n = (int)min((uint32_t)kBlock, todo - (uint32_t)r * kBlock);
         for (int j0 = 0; j0 < n; j0 += 32) {
           const int jt = j0 + lane;
           bool hit = false;
-          if (jt < n) hit = !(rect_dist2(s_xy[jt], x0f, x1f, y0f, y1f) > s_rc2[jt]);
+          if (jt < n) hit = !(rect_dist2(s_xy[b][jt], x0f, x1f, y0f, y1f) > s_rc2[b][jt]);
           uint32_t mask = __ballot_sync(0xffffffffu, hit);
           while (mask) {
             const int j = j0 + __ffs(mask) - 1;
@@ -512,7 +536,7 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
             bool active = index < last_contributor;
             float2 c; float4 co; float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
             if (active) {
-                c = s_xy[j]; co = s_co[j];
+                c = s_xy[b][j]; co = s_co[b][j];
                 dx = c.x - pxf; dy = c.y - pyf;
                 const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
                 if (power > 0.f) active = false;
@@ -530,7 +554,7 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
             if (active) {
                 T = T / (1.f - alpha);
                 const float dchannel_dcolor = alpha * T;
-                const float col0 = s_rgb[0][j], col1 = s_rgb[1][j], col2 = s_rgb[2][j];
+                const float col0 = s_rgb[b][0][j], col1 = s_rgb[b][1][j], col2 = s_rgb[b][2][j];
                 acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = col0;
                 acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = col1;
                 acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = col2;
@@ -551,19 +575,20 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
                 vo = G * dL_dalpha;
             }
             const float red = warp_reduce8(v, lane);
-            if ((lane & 3) == 0) atomicAdd(&s_acc[vidx][j], red);
+            if ((lane & 3) == 0) atomicAdd(&s_acc[b][vidx][j], red);
             if (kOpacity) {
                 vo = warp_sum(vo);
-                if (lane == 0) atomicAdd(&s_acc[8][j], vo);
+                if (lane == 0) atomicAdd(&s_acc[b][8][j], vo);
             }
           }
         }
+        if (more) stage(b ^ 1);      // buffer b^1 was last read in round r-1, whose barrier every warp has passed
         __syncthreads();
         if (have) {
-            const uint32_t g = s_id[tid];
+            const uint32_t g = s_id[b][tid];
             float a[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) { a[k] = s_acc[k][tid]; s_acc[k][tid] = 0.f; }
+            for (int k = 0; k < 9; ++k) { a[k] = s_acc[b][k][tid]; s_acc[b][k][tid] = 0.f; }      // reused in round r+2, after the next barrier
             if (a[0] != 0.f) atomicAdd(&d_colors[3 * (size_t)g], a[0]);
             if (a[1] != 0.f) atomicAdd(&d_colors[3 * (size_t)g + 1], a[1]);
             if (a[2] != 0.f) atomicAdd(&d_colors[3 * (size_t)g + 2], a[2]);

@@ -16,11 +16,17 @@ c = wl._cam_dev
 rs = GaussianRasterizationSettings(c.height, c.width, math.tan(c.FovX / 2), math.tan(c.FovY / 2), m.background, 1.0, c.world_view_transform,
                                    c.full_proj_transform, 0, c.camera_center, False, False)
 gw = torch.randn(3, c.height, c.width, device="cuda:0")
-for it in range(3):
+from gaussianavatar_b200 import _lib
+NIT = int(os.environ.get("GA_RASTER_ITERS", "3"))
+for it in range(NIT):
+    if it == 2: torch.cuda.synchronize(); _lib.profile(True)
     color, radii, ctx = rasterize_forward(means[0], colors[0], m.fix_opacity, scales[0], m.fix_rotation, rs)
     rasterize_backward(ctx, means[0].contiguous(), colors[0].contiguous(), scales[0].contiguous(), m.fix_rotation, rs, gw, want_opacity=False,
                        want_rotations=False, want_means2D=False)
 torch.cuda.synchronize()
+if NIT > 2:
+    rep = _lib.profile_report()
+    print("per-frame ms:", {k: round(t / (NIT - 2), 4) for k, (n, t) in rep.items() if "render" in k or "sort" in k})
 v = ctx.views()
 rg = v["ranges"].numpy().astype(np.int64)
 ln = rg[:, 1] - rg[:, 0]
