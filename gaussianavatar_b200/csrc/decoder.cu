@@ -25,10 +25,16 @@ int launch_conv_tc(int mode, const float *in, const float *w, float *out, int Hf
 int launch_round_tf32(const float *in, float *out, size_t n, cudaStream_t st);
 namespace {
 
-#ifndef GA_HEADS_CTAS_PER_SM
-#define GA_HEADS_CTAS_PER_SM 2
+#ifndef GA_HEADS_MINB
+#define GA_HEADS_MINB 2
 #endif
-constexpr int kHeadsGrid = GA_HEADS_CTAS_PER_SM * kNumSMs;   // grid-stride CTAs of the heads kernels (2 per SM measured best: 4/6/8 lose to the per-CTA weight-gradient flush)
+#ifndef GA_HEADS_UNROLL
+#define GA_HEADS_UNROLL 4
+#endif
+#ifndef GA_HEADS_CTAS_PER_SM
+#define GA_HEADS_CTAS_PER_SM GA_HEADS_MINB
+#endif
+constexpr int kHeadsGrid = GA_HEADS_CTAS_PER_SM * kNumSMs;   // grid-stride CTAs of the heads kernels (= resident CTAs per SM at <= 80 registers)
 constexpr int kCg = 64;        // c_geom
 constexpr int kH = 128;        // hsize
 constexpr int kFeatLd = 72;    // 64 sampled + 2 uv + 6 zero pad (multiple of 8)
@@ -245,58 +251,92 @@ __global__ void bn_finalize_bwd_kernel(int C, double count, const double *__rest
     d_beta[c] = (float)s1[c];
 }
 
-// Final 1x1 convs of the three heads (conv8 128->3, conv8N 128->1 + sigmoid, conv8SH 128->3 + sigmoid,
-// modules.py:566-580) fused with the last BN + Softplus: 8 lanes per pixel, 16 channels per lane and head.
+// softplus(z) and sigmoid(z) from ONE exponential: e = exp(-|z|); softplus = max(z,0) + log(1+e); sigmoid = (z >= 0 ? 1 : e) / (1 + e).
+// FAST (TF32 path): 3 MUFU ops (ex2, lg2, rcp); exact path: the fp32 library forms the parity tests are written against.
 template <bool FAST>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void softplus_sigmoid(float z, float &sp, float &sg)
+{
+    if (FAST) {
+        const float e = __expf(-fabsf(z)), d = 1.f + e;
+        sp = fmaxf(z, 0.f) + __logf(d);
+        sg = __fdividef(z >= 0.f ? 1.f : e, d);
+    } else {
+        sp = softplus_f(z);
+        sg = sigmoid_f(z);
+    }
+}
+
+// Sum 8 per-lane values over the warp with 9 shuffles (recursive halving, same scheme as the rasterizer's gradient reduction):
+// returns the total of value idx = 4*bit4(lane) + 2*bit3(lane) + bit2(lane), replicated over the lane's 4-lane group.
+__device__ __forceinline__ float heads_reduce8(float (&v)[8], int lane)
+{
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float send = h4 ? v[i] : v[i + 4]; v[i] = (h4 ? v[i + 4] : v[i]) + __shfl_xor_sync(0xffffffffu, send, 16); }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { const float send = h3 ? v[i] : v[i + 2]; v[i] = (h3 ? v[i + 2] : v[i]) + __shfl_xor_sync(0xffffffffu, send, 8); }
+    { const float send = h2 ? v[0] : v[1]; v[0] = (h2 ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, send, 4); }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+    return v[0];
+}
+
+
+// Final 1x1 convs of the three heads (conv8 128->3, conv8N 128->1 + sigmoid, conv8SH 128->3 + sigmoid,
+// modules.py:566-580) fused with the last BN + Softplus.  One warp per pixel, lane = 4 channels of each head (every
+// coefficient is a thread constant; a pixel's 1.5 KB is three 512-byte warp loads), 7 dot products reduced with 9 shuffles.
+template <bool FAST>
+__global__ void __launch_bounds__(256, GA_HEADS_MINB)
 heads_fwd_kernel(size_t M, const float *__restrict__ Y7 /*[M,384]*/, const float *__restrict__ a7, const float *__restrict__ b7,
                  const float *__restrict__ W8 /*[8,128]*/, const float *__restrict__ b8, float *__restrict__ dec /*[M,8]*/)
 {
-    __shared__ float sW[8][kH], sa[3 * kH], sb[3 * kH];
-    for (int i = threadIdx.x; i < 8 * kH; i += 256) sW[i / kH][i % kH] = W8[i];
-    for (int i = threadIdx.x; i < 3 * kH; i += 256) { sa[i] = a7[i]; sb[i] = b7[i]; }
-    __syncthreads();
-    const int l = threadIdx.x & 7;
-    const size_t stride = (size_t)gridDim.x * 32;
-    for (size_t m = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); m < M; m += stride) {
-        float p[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int lane = threadIdx.x & 31, c = lane * 4;
+    float4 A[3], B[3], Wv[7];
 #pragma unroll
-        for (int h = 0; h < 3; ++h)
+    for (int h = 0; h < 3; ++h) { A[h] = *reinterpret_cast<const float4 *>(a7 + h * kH + c); B[h] = *reinterpret_cast<const float4 *>(b7 + h * kH + c); }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = l * 4 + 32 * i;
-                const float4 y = *reinterpret_cast<const float4 *>(Y7 + m * 3 * kH + h * kH + c);
-                const float z4[4] = {fmaf(y.x, sa[h * kH + c], sb[h * kH + c]), fmaf(y.y, sa[h * kH + c + 1], sb[h * kH + c + 1]),
-                                     fmaf(y.z, sa[h * kH + c + 2], sb[h * kH + c + 2]), fmaf(y.w, sa[h * kH + c + 3], sb[h * kH + c + 3])};
+    for (int o = 0; o < 7; ++o) Wv[o] = *reinterpret_cast<const float4 *>(W8 + o * kH + c);
+    const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);      // output this lane ends up holding
+    const float bias = idx < 7 ? b8[idx] : 0.f;
+    const size_t nwarps = (size_t)gridDim.x * 8;
+    for (size_t mb = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); mb < M; mb += 2 * nwarps) {
+        float4 yy[2][3];                                                  // two pixels per trip: six 512-byte warp loads in flight
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int h = 0; h < 3; ++h)
+                yy[u][h] = (mb + u * nwarps < M) ? *reinterpret_cast<const float4 *>(Y7 + (mb + u * nwarps) * 3 * kH + h * kH + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const size_t m = mb + u * nwarps;
+            if (m >= M) break;
+            float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                const float4 y = yy[u][h];
+                const float z4[4] = {fmaf(y.x, A[h].x, B[h].x), fmaf(y.y, A[h].y, B[h].y), fmaf(y.z, A[h].z, B[h].z), fmaf(y.w, A[h].w, B[h].w)};
                 float x[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) x[e] = FAST ? softplus_fast(z4[e]) : softplus_f(z4[e]);
+                constexpr int o0[3] = {0, 3, 4}, no[3] = {3, 1, 3};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (h == 0) { p[0] = fmaf(x[e], sW[0][c + e], p[0]); p[1] = fmaf(x[e], sW[1][c + e], p[1]); p[2] = fmaf(x[e], sW[2][c + e], p[2]); }
-                    else if (h == 1) { p[3] = fmaf(x[e], sW[3][c + e], p[3]); }
-                    else { p[4] = fmaf(x[e], sW[4][c + e], p[4]); p[5] = fmaf(x[e], sW[5][c + e], p[5]); p[6] = fmaf(x[e], sW[6][c + e], p[6]); }
-                }
+                for (int o = 0; o < 3; ++o)
+                    if (o < no[h]) {
+                        const float4 w = Wv[o0[h] + o];
+                        p[o0[h] + o] = fmaf(x[0], w.x, fmaf(x[1], w.y, fmaf(x[2], w.z, x[3] * w.w)));
+                    }
             }
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            p[k] += __shfl_xor_sync(0xffffffffu, p[k], 1);
-            p[k] += __shfl_xor_sync(0xffffffffu, p[k], 2);
-            p[k] += __shfl_xor_sync(0xffffffffu, p[k], 4);
-        }
-        if (l == 0) {
-            const float4 o0 = make_float4(p[0] + b8[0], p[1] + b8[1], p[2] + b8[2], sigmoid_f(p[3] + b8[3]));
-            const float4 o1 = make_float4(sigmoid_f(p[4] + b8[4]), sigmoid_f(p[5] + b8[5]), sigmoid_f(p[6] + b8[6]), 0.f);
-            *reinterpret_cast<float4 *>(dec + m * 8) = o0;
-            *reinterpret_cast<float4 *>(dec + m * 8 + 4) = o1;
+            const float r = heads_reduce8(p, lane) + bias;
+            if ((lane & 3) == 0) dec[m * 8 + idx] = idx < 3 ? r : (idx < 7 ? sigmoid_f(r) : 0.f);
         }
     }
 }
 
 // Backward of one head's final conv (+ sigmoid) and of the BN+Softplus feeding it.  HEAD 0: xyz (rows 0-2),
 // 1: scale (row 3), 2: colour (rows 4-6).  Writes dZ7[:, head*128 ...], accumulates s1/s2 (double), dW8 rows, db8.
+// One warp per pixel, lane = 4 channels: the running sums for dW8 / BatchNorm statistics are 4 x (NOUT + 2) registers.
 template <int HEAD, bool FAST>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GA_HEADS_MINB)
 heads_bwd_kernel(size_t M, const float *__restrict__ Y7, const float *__restrict__ a7, const float *__restrict__ b7,
                  const float *__restrict__ mu7, const float *__restrict__ rstd7, const float *__restrict__ W8,
                  const float *__restrict__ dec, const float *__restrict__ d_dec, float *__restrict__ dZ7,
@@ -304,67 +344,75 @@ heads_bwd_kernel(size_t M, const float *__restrict__ Y7, const float *__restrict
 {
     constexpr int NOUT = (HEAD == 1) ? 1 : 3;
     constexpr int ROW0 = (HEAD == 0) ? 0 : (HEAD == 1 ? 3 : 4);
-    __shared__ float sW[NOUT][kH], sa[kH], sb[kH], smu[kH], srs[kH];
     __shared__ float sacc[NOUT + 2][kH];
     __shared__ float sdb[NOUT];
-    for (int i = threadIdx.x; i < NOUT * kH; i += 256) sW[i / kH][i % kH] = W8[(ROW0 + i / kH) * kH + i % kH];
-    for (int i = threadIdx.x; i < kH; i += 256) {
-        sa[i] = a7[HEAD * kH + i]; sb[i] = b7[HEAD * kH + i]; smu[i] = mu7[HEAD * kH + i]; srs[i] = rstd7[HEAD * kH + i];
-    }
     for (int i = threadIdx.x; i < (NOUT + 2) * kH; i += 256) sacc[i / kH][i % kH] = 0.f;
     if (threadIdx.x < NOUT) sdb[threadIdx.x] = 0.f;
     __syncthreads();
-    const int l = threadIdx.x & 7;
-    float aw[NOUT][16], a1[16], a2[16], adb[NOUT];
+    const int lane = threadIdx.x & 31, c = lane * 4;
+    const float4 av = *reinterpret_cast<const float4 *>(a7 + HEAD * kH + c), bv = *reinterpret_cast<const float4 *>(b7 + HEAD * kH + c);
+    const float4 muv = *reinterpret_cast<const float4 *>(mu7 + HEAD * kH + c), rsv = *reinterpret_cast<const float4 *>(rstd7 + HEAD * kH + c);
+    const float a_[4] = {av.x, av.y, av.z, av.w}, b_[4] = {bv.x, bv.y, bv.z, bv.w}, mu_[4] = {muv.x, muv.y, muv.z, muv.w},
+                rs_[4] = {rsv.x, rsv.y, rsv.z, rsv.w};
+    float w_[NOUT][4];
 #pragma unroll
-    for (int o = 0; o < NOUT; ++o) { adb[o] = 0.f;
+    for (int o = 0; o < NOUT; ++o) {
+        const float4 w = *reinterpret_cast<const float4 *>(W8 + (ROW0 + o) * kH + c);
+        w_[o][0] = w.x; w_[o][1] = w.y; w_[o][2] = w.z; w_[o][3] = w.w;
+    }
+    float aw[NOUT][4], a1[4], a2[4], adb[NOUT];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) aw[o][k] = 0.f; }
+    for (int o = 0; o < NOUT; ++o) { adb[o] = 0.f; aw[o][0] = aw[o][1] = aw[o][2] = aw[o][3] = 0.f; }
 #pragma unroll
-    for (int k = 0; k < 16; ++k) a1[k] = a2[k] = 0.f;
+    for (int e = 0; e < 4; ++e) a1[e] = a2[e] = 0.f;
 
-    const size_t stride = (size_t)gridDim.x * 32;
-    for (size_t m = (size_t)blockIdx.x * 32 + (threadIdx.x >> 3); m < M; m += stride) {
-        float dp[NOUT];
+    const size_t nwarps = (size_t)gridDim.x * 8;
+    constexpr int U = GA_HEADS_UNROLL;                                    // pixels per trip: U 512-byte warp loads in flight
+    for (size_t mb = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); mb < M; mb += U * nwarps) {
+        float4 yv[U]; float dpv[U][NOUT];
 #pragma unroll
-        for (int o = 0; o < NOUT; ++o) {
-            const float g = d_dec[m * 8 + ROW0 + o];
-            if (HEAD == 0) dp[o] = g;                                    // conv8: no output activation
-            else { const float s = dec[m * 8 + ROW0 + o]; dp[o] = g * s * (1.f - s); }   // sigmoid backward
+        for (int u = 0; u < U; ++u) {
+            const size_t m = mb + u * nwarps;
+            const bool ok = m < M;
+            yv[u] = ok ? *reinterpret_cast<const float4 *>(Y7 + m * 3 * kH + HEAD * kH + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int o = 0; o < NOUT; ++o) {                             // same address for every lane: one broadcast transaction
+                const float g = ok ? d_dec[m * 8 + ROW0 + o] : 0.f;
+                if (HEAD == 0) dpv[u][o] = g;                            // conv8: no output activation
+                else { const float sv = ok ? dec[m * 8 + ROW0 + o] : 0.f; dpv[u][o] = g * sv * (1.f - sv); }   // sigmoid backward
+            }
         }
 #pragma unroll
-        for (int o = 0; o < NOUT; ++o) adb[o] += (l == 0) ? dp[o] : 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = l * 4 + 32 * i;
-            const float4 y4 = *reinterpret_cast<const float4 *>(Y7 + m * 3 * kH + HEAD * kH + c);
-            const float y[4] = {y4.x, y4.y, y4.z, y4.w};
+        for (int u = 0; u < U; ++u) {
+            const size_t m = mb + u * nwarps;
+            if (m >= M) break;
+            const float y[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
             float dz[4];
 #pragma unroll
+            for (int o = 0; o < NOUT; ++o) adb[o] += dpv[u][o];
+#pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const float z = fmaf(y[e], sa[c + e], sb[c + e]);
-                const float x = FAST ? softplus_fast(z) : softplus_f(z);
+                const float z = fmaf(y[e], a_[e], b_[e]);
+                float x, sg;
+                softplus_sigmoid<FAST>(z, x, sg);
                 float dx = 0.f;
 #pragma unroll
-                for (int o = 0; o < NOUT; ++o) { dx = fmaf(dp[o], sW[o][c + e], dx); aw[o][i * 4 + e] = fmaf(dp[o], x, aw[o][i * 4 + e]); }
-                dz[e] = dx * (FAST ? sigmoid_fast(z) : sigmoid_f(z));
-                a1[i * 4 + e] += dz[e];
-                a2[i * 4 + e] = fmaf(dz[e], (y[e] - smu[c + e]) * srs[c + e], a2[i * 4 + e]);
+                for (int o = 0; o < NOUT; ++o) { dx = fmaf(dpv[u][o], w_[o][e], dx); aw[o][e] = fmaf(dpv[u][o], x, aw[o][e]); }
+                dz[e] = dx * sg;
+                a1[e] += dz[e];
+                a2[e] = fmaf(dz[e], (y[e] - mu_[e]) * rs_[e], a2[e]);
             }
             *reinterpret_cast<float4 *>(dZ7 + m * 3 * kH + HEAD * kH + c) = make_float4(dz[0], dz[1], dz[2], dz[3]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int e = 0; e < 4; ++e) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int c = l * 4 + 32 * i + e;
-#pragma unroll
-            for (int o = 0; o < NOUT; ++o) atomicAdd(&sacc[o][c], aw[o][i * 4 + e]);
-            atomicAdd(&sacc[NOUT][c], a1[i * 4 + e]);
-            atomicAdd(&sacc[NOUT + 1][c], a2[i * 4 + e]);
-        }
-    if (l == 0) {
+        for (int o = 0; o < NOUT; ++o) atomicAdd(&sacc[o][c + e], aw[o][e]);
+        atomicAdd(&sacc[NOUT][c + e], a1[e]);
+        atomicAdd(&sacc[NOUT + 1][c + e], a2[e]);
+    }
+    if (lane == 0) {
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) atomicAdd(&sdb[o], adb[o]);
     }
