@@ -228,20 +228,26 @@ def main():
         torch.cuda.synchronize()
 
     def run_value(n, start):
+        t0 = time.perf_counter()
         for i in range(n):
             batch = wl.device_batch(wl.frame_ids(start + i, rank, world))
             trainer.step(batch, iteration0 + start + i, epoch=1)
+        if os.environ.get("GA_BENCH_DIAG") == "1" and rank == 0 and n > 2:
+            print(f"value diag (rank 0): host enqueue loop {1e3 * (time.perf_counter() - t0) / n:.2f} ms per step", file=sys.stderr, flush=True)
 
     h2d_bytes = [0]
     copy_stream = torch.cuda.Stream(device=dev)
-    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(4)]
 
     def run_e2e(n, start):
         """Public-API loop with HOST batches: the next batch's H2D copy (pinned -> device, side stream) is prefetched while
         the current step computes, as a DataLoader with pin_memory would; every step's loss is copied back to pinned host
-        memory and read one step later (so the read-back never stalls the enqueue).  All of it is inside the timed region."""
+        memory and read two steps later (so the read-back never stalls the enqueue).  All of it is inside the timed region."""
         last = 0.0
-        pending = None
+        lag = int(os.environ.get("GA_E2E_LAG", "2"))           # the loss of step i is read when step i + lag has been enqueued
+        diag = os.environ.get("GA_BENCH_DIAG") == "1" and rank == 0
+        t_fetch = t_step = t_wait = 0.0
+        pending = []
 
         def fetch(i):
             hb = wl.host_batch(wl.frame_ids(start + i, rank, world))
@@ -253,6 +259,7 @@ def main():
 
         nxt = fetch(0)
         for i in range(n):
+            t0 = time.perf_counter()
             batch, ev = nxt
             torch.cuda.current_stream().wait_event(ev)
             for t in batch.values():
@@ -260,14 +267,22 @@ def main():
                     t.record_stream(torch.cuda.current_stream())
             if i + 1 < n:
                 nxt = fetch(i + 1)
+            t1 = time.perf_counter()
             loss = trainer.step(batch, iteration0 + start + i, epoch=1)
-            buf = loss_host[i & 1]
+            buf = loss_host[i % len(loss_host)]
             buf.copy_(loss.detach(), non_blocking=True)        # device -> host read of the step's result (train.py:101)
             done = torch.cuda.Event(); done.record()
-            if pending is not None:
-                pending[1].synchronize(); last = float(pending[0])
-            pending = (buf, done)
-        pending[1].synchronize(); last = float(pending[0])
+            t2 = time.perf_counter()
+            pending.append((buf, done))
+            if len(pending) > lag:
+                b0, d0 = pending.pop(0)
+                d0.synchronize(); last = float(b0)
+            t3 = time.perf_counter()
+            t_fetch += t1 - t0; t_step += t2 - t1; t_wait += t3 - t2
+        for b0, d0 in pending:
+            d0.synchronize(); last = float(b0)
+        if diag and n > 2:
+            print(f"e2e diag (rank 0, per step): fetch {1e3 * t_fetch / n:.2f} ms, enqueue {1e3 * t_step / n:.2f} ms, wait {1e3 * t_wait / n:.2f} ms", file=sys.stderr, flush=True)
         return last
 
     def timed(fn, n, start):
