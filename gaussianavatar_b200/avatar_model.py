@@ -204,15 +204,39 @@ class AvatarModel:
         means, scales, colors = LbsAssemble.apply(dec, cano2live, self.valid_index, self._query_points, self._query_lbs, scale_mul)
         return means, scales, colors, dec
 
+    def _render_one(self, batch_data, means, scales, colors, b):
+        return render_batch(points=means[b], shs=None, colors_precomp=colors[b], rotations=self.fix_rotation,
+                            scales=scales[b], opacity=self.fix_opacity, FovX=batch_data["FovX"][b], FovY=batch_data["FovY"][b],
+                            height=batch_data["height"][b], width=batch_data["width"][b], bg_color=self.background,
+                            world_view_transform=batch_data["world_view_transform"][b],
+                            full_proj_transform=batch_data["full_proj_transform"][b], active_sh_degree=0,
+                            camera_center=batch_data["camera_center"][b])
+
     def _render_frames(self, batch_data, means, scales, colors):
+        """The reference rasterizes the frames of a batch one after the other (avatar_model.py:332-365).  Frames are independent, and
+        the compositing kernels end in a long tail of a few crowded tiles, so consecutive frames go to two alternating side
+        streams: frame b+1's preprocess / sort (and, in the backward, its replay) fill the SMs frame b's tail leaves idle.
+        autograd runs each frame's backward on the stream of its forward.  GA_FRAME_STREAMS=0 keeps everything on one stream."""
+        B = means.shape[0]
+        if B < 2 or not means.is_cuda or os.environ.get("GA_FRAME_STREAMS", "1") == "0":
+            return torch.stack([self._render_one(batch_data, means, scales, colors, b) for b in range(B)], dim=0)
+        main = torch.cuda.current_stream()
+        if getattr(self, "_frame_streams", None) is None:
+            self._frame_streams = [torch.cuda.Stream(device=means.device) for _ in range(2)]
+        ready = torch.cuda.Event()
+        ready.record(main)
         images = []
-        for b in range(means.shape[0]):
-            images.append(render_batch(points=means[b], shs=None, colors_precomp=colors[b], rotations=self.fix_rotation,
-                                       scales=scales[b], opacity=self.fix_opacity, FovX=batch_data["FovX"][b], FovY=batch_data["FovY"][b],
-                                       height=batch_data["height"][b], width=batch_data["width"][b], bg_color=self.background,
-                                       world_view_transform=batch_data["world_view_transform"][b],
-                                       full_proj_transform=batch_data["full_proj_transform"][b], active_sh_degree=0,
-                                       camera_center=batch_data["camera_center"][b]))
+        for b in range(B):
+            s = self._frame_streams[b % 2]
+            s.wait_event(ready)                       # means / scales / colours were produced on the main stream
+            with torch.cuda.stream(s):
+                img = self._render_one(batch_data, means, scales, colors, b)
+            img.record_stream(main)
+            images.append(img)
+        for s in self._frame_streams[:min(B, 2)]:
+            for t in (means, scales, colors):
+                t.record_stream(s)
+            main.wait_stream(s)
         return torch.stack(images, dim=0)
 
     def train_stage1(self, batch_data, iteration):
