@@ -356,12 +356,19 @@ def main():
     mlp_ms = kms("mlp_tc_fwd", "mlp_tc_bwd") + sum(v[1] for k, v in per_step.items() if k.startswith("mlp_") and not k.startswith("mlp_tc"))
     dominant = max(per_step.items(), key=lambda kv: kv[1][1])[0] if per_step else None
 
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (a 128 -> 128 layer at config-3 size) from the committed `ncu --set full`
+    # captures (profiles/r1_tc_bwd_ncu.md, profiles/r1_tc_fwd_ncu.md); the same launch's algorithmic bytes are 4 (bwd) / 2 (fwd) planes
+    ncu_traffic = {"mlp_tc_bwd": (402.866e6 + 111.877e6, 4 * plane), "mlp_tc_fwd": (134.399e6 + 84.248e6, 2 * plane)} if (wl.S, wl.side) == (512, 1024) else {}
+
     def hbm_roof(name, nbytes, label):
         ms = kms(name)
         n = per_step[name][0] if name in per_step else 0
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
+        tr = ncu_traffic.get(name)
         return {"kernel": label, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": gbs / peaks["hbm_gbs"] if gbs else None, "traffic": None, "launches_per_step": n, "ms_per_step": ms,
+                "frac": gbs / peaks["hbm_gbs"] if gbs else None, "traffic": tr[0] if tr else None,
+                "traffic_note": (f"ncu dram bytes of one 128->128 layer launch; algorithmic bytes of that launch: {tr[1]:.0f}" if tr else None),
+                "launches_per_step": n, "ms_per_step": ms,
                 "avg_launch_ms": ms / n if n else None, "algorithmic_bytes_per_step": nbytes,
                 "share_of_kernel_time": ms / total_kernel_ms if total_kernel_ms else None, "peak_source": peaks["_source"]}
 
