@@ -160,15 +160,33 @@ class AvatarModel:
             self.pose.load_state_dict(saved["pose"], strict=False)
             self.transl.load_state_dict(saved["transl"], strict=False)
         self.geo_feature.data[...] = saved["geo_feature"].data[...]
-        # optimizer state: only restorable when it was written by this implementation (one flat parameter); a reference
-        # checkpoint's per-tensor Adam moments are dropped
+        # optimizer state: written either by this implementation (ONE flat net parameter + geo_feature) or by the reference
+        # (53 per-tensor Adam states + geo_feature, avatar_model.py:148-155): the latter is re-laid out into the flat buffer
         if self.optimizer is not None and "optimizer" in saved:
-            try:
-                self.optimizer.load_state_dict(saved["optimizer"])
-            except (ValueError, KeyError):
-                pass
+            self.optimizer.load_state_dict(self.translate_optimizer_state(saved["optimizer"]))
         if self.scheduler is not None and "scheduler" in saved:
             self.scheduler.load_state_dict(saved["scheduler"])
+
+    def translate_optimizer_state(self, osd):
+        """A `torch.optim.Adam.state_dict()` over the reference's parameter list -> the same over (net.flat, geo_feature).
+        State dicts already in this implementation's layout pass through unchanged."""
+        from .network import REFERENCE_PARAM_ORDER
+        groups = osd["param_groups"]
+        n_ref = len(REFERENCE_PARAM_ORDER)
+        if not (len(groups) == 2 and len(groups[0]["params"]) == n_ref and len(groups[1]["params"]) == 1):
+            return osd
+        ids, geo_id = list(groups[0]["params"]), groups[1]["params"][0]
+        state = osd.get("state", {})
+        new_state = {}
+        if all(i in state for i in ids):
+            new_state[0] = {"step": state[ids[0]]["step"],
+                            "exp_avg": self.net.flat_from_reference_tensors([state[i]["exp_avg"] for i in ids]),
+                            "exp_avg_sq": self.net.flat_from_reference_tensors([state[i]["exp_avg_sq"] for i in ids])}
+        if geo_id in state:
+            new_state[1] = dict(state[geo_id])
+        g0, g1 = dict(groups[0]), dict(groups[1])
+        g0["params"], g1["params"] = [0], [1]
+        return {"state": new_state, "param_groups": [g0, g1]}
 
     def stage_load(self, ckpt_path):
         saved = torch.load(os.path.join(ckpt_path, "net.pth"), weights_only=False)

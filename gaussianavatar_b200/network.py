@@ -20,6 +20,14 @@ from . import _lib
 from .ops import DecoderNet
 
 _HEADS = ("", "N", "SH")          # head order inside the stacked layers: xyz, scale (N), colour (SH)
+
+# Order of the reference's `net.parameters()` (module registration order of POP_no_unet / ShapeDecoder, model/network.py:18-36,
+# model/modules.py:477-528): the indices of torch.optim.Adam's state in a reference checkpoint refer to it
+# (model/avatar_model.py:148-155,163-176).  Pinned by tests/golden/pop_param_order.json (generated from the reference).
+REFERENCE_PARAM_ORDER = tuple(
+    [f"geom_proc_layers.conv{k}.weight" for k in (1, 2, 3)]
+    + [f"decoder.conv{l}{sfx}.{wb}" for sfx, ls in (("", range(1, 9)), ("SH", (6, 7, 8)), ("N", (6, 7, 8))) for l in ls for wb in ("weight", "bias")]
+    + [f"decoder.bn{l}{sfx}.{wb}" for sfx, ls in (("", range(1, 8)), ("N", (6, 7)), ("SH", (6, 7))) for l in ls for wb in ("weight", "bias")])
 _BN_LAYERS = ["bn1", "bn2", "bn3", "bn4", "bn5", "bn6", "bn6N", "bn6SH", "bn7", "bn7N", "bn7SH"]
 
 
@@ -147,6 +155,26 @@ class POP_no_unet(nn.Module):
         if self.flat.grad is None:
             return OrderedDict()
         return OrderedDict((k, get().detach().clone()) for k, (get, _) in self._slots(self.flat.grad).items() if "running" not in k)
+
+    def flat_from_reference_tensors(self, tensors) -> torch.Tensor:
+        """Scatter per-parameter tensors given in REFERENCE_PARAM_ORDER (e.g. the exp_avg / exp_avg_sq of a reference
+        checkpoint's Adam state) into a new buffer laid out like `self.flat`; padding elements stay zero."""
+        if len(tensors) != len(REFERENCE_PARAM_ORDER):
+            raise ValueError(f"expected {len(REFERENCE_PARAM_ORDER)} per-parameter tensors, got {len(tensors)}")
+        buf = torch.zeros_like(self.flat.data)
+        slots = self._slots(buf)
+        for name, t in zip(REFERENCE_PARAM_ORDER, tensors):
+            get, put = slots[name]
+            t = torch.as_tensor(t).to(device=buf.device, dtype=buf.dtype)
+            if tuple(get().shape) != tuple(t.shape):
+                raise ValueError(f"{name}: expected shape {tuple(get().shape)}, got {tuple(t.shape)}")
+            put(t)
+        return buf
+
+    def reference_tensors_from_flat(self, flat) -> "list[torch.Tensor]":
+        """Inverse of flat_from_reference_tensors: views/copies of a flat-layout buffer under the reference's parameter order."""
+        slots = self._slots(flat)
+        return [slots[name][0]().detach().clone() for name in REFERENCE_PARAM_ORDER]
 
     def state_dict(self, *args, destination=None, prefix="", keep_vars=False, **kw):
         sd = OrderedDict() if destination is None else destination

@@ -119,6 +119,18 @@ def gen_camera():
     np.savez_compressed(os.path.join(OUT, "camera.npz"), **out)
 
 
+def gen_param_order():
+    """Parameter order of the reference's `net.parameters()` (what torch.optim.Adam's state indices refer to in a reference
+    checkpoint, model/avatar_model.py:148-155,163-176): pins gaussianavatar_b200.network.REFERENCE_PARAM_ORDER."""
+    import json
+    net = POP_no_unet(c_geom=64, geom_layer_type="conv", nf=64, hsize=128, up_mode="upconv", use_dropout=False, uv_feat_dim=2)
+    order = [[n, list(p.shape)] for n, p in net.named_parameters()]
+    with open(os.path.join(OUT, "pop_param_order.json"), "w") as f:
+        json.dump(order, f, indent=0)
+    print("pop_param_order.json", len(order))
+
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_test_pose_subset()
@@ -126,5 +138,6 @@ if __name__ == "__main__":
     gen_pop()
     gen_losses()
     gen_camera()
+    gen_param_order()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
