@@ -1,16 +1,20 @@
 // Decoder-MLP layers on the 5th-generation tensor cores (tcgen05, kind::tf32, accumulators in TMEM).
 //
 // One persistent, warp-specialised CTA per SM computes  Y[M,128] (+)= act(bn(X))[M,K] * W[128,K]^T + bias  for its share
-// of 128-pixel tiles:
-//   warps 0-7  producers : coalesced LDG of the raw (pre-BatchNorm) input tile, BatchNorm + Softplus applied in
-//                          registers, STS into the 128-byte-swizzled K-major UMMA layout, fence.proxy.async, mbarrier
-//   warp  8    MMA issuer: one elected lane issues K/8 tcgen05.mma (M=128, N=128, K=8) per tile into one of two TMEM
-//                          accumulators, tcgen05.commit -> mbarrier
-//   warps 9-12 epilogue  : tcgen05.ld the accumulator (lane = pixel row), + bias, stage the tile in the just-consumed
-//                          input buffer (XOR-swizzled, conflict-free both ways), coalesced global stores, per-channel
-//                          sum / sum-of-squares for the layer's BatchNorm (fp32 per tile, double across tiles)
-// Two input stages + two accumulators overlap load/transform, MMA and store.  The layer is HBM-bound (64 KB in + 64 KB
-// out per 2.1 MFLOP... DESIGN.md §4), so the point of the tensor core here is to take the math off the critical path.
+// of 128-pixel tiles (17 warps):
+//   warps 0-7   producers : 16 coalesced LDG.128 per thread in flight for the raw (pre-BatchNorm) input tile, BatchNorm +
+//                           Softplus applied in registers (log2 domain), STS.128 into the 128-byte-swizzled K-major UMMA
+//                           layout, fence.proxy.async, mbarrier
+//   warp  8     MMA issuer: one elected lane issues K/8 tcgen05.mma (M=128, N=128, K=8) per tile into one of two TMEM
+//                           accumulators, tcgen05.commit -> mbarrier
+//   warps 9-16  epilogue  : two warps per TMEM lane quarter, half the channels each: tcgen05.ld (lane = pixel row), stage the
+//                           tile in the just-consumed input buffer (XOR-swizzled, conflict-free both ways), then one
+//                           coalesced 512-byte row per warp instruction: + bias, global store, and the layer's BatchNorm
+//                           sum / sum-of-squares accumulated in the same loop (float4 per lane per tile, double across
+//                           tiles, combined through shared memory: 2 atomics per channel per CTA)
+// Two input stages + two accumulators overlap load/transform, MMA and store.  The layer moves 64 KB in + 64 KB out per
+// 4.2 MFLOP tile: the tensor core takes the math off the critical path, what is left is latency / issue bound
+// (profiles/r1_tc_fwd_ncu.md), which is why the warp counts per role were tuned on the device (tools/variants.py).
 //
 // TF32 is what the reference computes these 1x1 convolutions in on any Ampere+ GPU (cuDNN allow_tf32 default,
 // SURVEY.md §8 a-4); the strict-FP32 CUDA-core path (gemm.cuh) remains selectable and is the GPU-side reference.
@@ -317,16 +321,16 @@ extern "C" int ga_tc_linear_forward(int32_t M, int32_t K, const float *X, int32_
 //
 //   G  = dY_l      [px, out] = ga (dZ_l - m1 - xhat_l m2)          BatchNorm backward applied while loading (dZ_l, Y_l)
 //   X  = x_l       [px, in ] = softplus(a Y_{l-1} + b)             recomputed while loading Y_{l-1}
-//   dW_l [out,in] += G^T X      A = G^T [out rows][px], B = X^T [in rows][px]  (both K-major: the producers write the
-//                               TRANSPOSED tiles); the accumulator lives in TMEM for the whole kernel, one flush at the end
-//   dX^T [in, px]  = W_l^T G^T  A = W_l^T [in rows][out] (transposed once per CTA), B = G [px rows][out]; computed
+//   dW_l [out,in] += G^T X      K = pixel: A = G and B = X are consumed MN-major straight from their pixel-major images
+//                               (128-byte swizzle with a 32-byte base, UMMA layout type 1); the accumulator lives in TMEM for
+//                               the whole kernel, one flush (16-byte vector reductions) at the end
+//   dX^T [in, px]  = W_l^T G^T  A = W_l^T [in rows][out] (transposed once per CTA), B = G [px rows][out] K-major; computed
 //                               TRANSPOSED so that a TMEM lane is an input channel: the epilogue thread's BatchNorm
 //                               scalars are constants and sum(dZ), sum(dZ xhat) need no cross-thread reduction
-//   dZ_{l-1} = dX * sigmoid(z_{l-1})   (z_{l-1}, xhat_{l-1} from a coalesced, L2-hot re-read of Y_{l-1})
-// Every operand is K-major with the 128-byte swizzle (MN-major TF32 would need the 32-byte-base swizzle, i.e. a second
-// physical layout, so transposing in the producers' stores is the cheaper route: ~640 shared-memory wavefronts per tile
-// against an HBM budget of ~2800 cycles).  32-pixel tiles, three stages, 13 warps: 4 producers for G, 4 for X, 1 MMA
-// issuer, 4 epilogue.
+//   dZ_{l-1} = dX * sigmoid(z_{l-1})   (sigmoid(z_{l-1}) and xhat_{l-1} recovered from x = softplus(z) in the X tile: no re-read)
+// G is stored in two swizzles of the same [px][channel] image (K-major operands reject layout type 1), X once; every store
+// is a conflict-free STS.128 of a full 128-byte row and every global load a full line.  32-pixel tiles, three stages,
+// 25 warps: 8 producers for G, 8 for X, 1 MMA issuer, 8 epilogue (two per TMEM lane quarter, 16 pixels each).
 // =====================================================================================================================
 namespace ga {
 namespace {
