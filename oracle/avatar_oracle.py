@@ -228,3 +228,52 @@ def seeded_pop_params(seed: int, c_geom=64, hsize=128, dtype=torch.float32) -> d
             bound = 1.0 / math.sqrt(fan_in)
             p[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
     return {k: v.to(dtype) for k, v in p.items()}
+
+
+# ---- stage 2: pose encoder (next scope row) -----------------------------------------------------------------
+def bn_train_noaffine(x, eps=1e-5):
+    """nn.BatchNorm2d(affine=False) in training mode (modules.py:69,98): per-channel batch statistics, biased variance."""
+    mean = x.mean(dim=(0, 2, 3), keepdim=True)
+    var = x.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
+    return (x - mean) / torch.sqrt(var + eps)
+
+
+def unet5ds_forward(p: dict, x: torch.Tensor) -> torch.Tensor:
+    """UnetNoCond5DS.forward (model/modules.py:185-232; called at model/avatar_model.py:401,589) with up_mode='upconv', no
+    dropout, training-mode BatchNorm.  Blocks: Conv2DBlock = [LeakyReLU(0.2)] -> conv4x4 s2 p1 -> [BN] (modules.py:62-78),
+    UpConv2DBlock = ReLU -> ConvTranspose4x4 s2 p1 -> [BN] -> cat(skip) (modules.py:81-111).
+    Reference quirk reproduced: Conv2DBlock's LeakyReLU is `inplace=True`, so it also rewrites its INPUT tensor -- the skip
+    connections d1..d4 that reach the up path are the leaky-ReLU'd activations, not the raw conv / BN outputs."""
+    lrelu = lambda t: F.leaky_relu(t, 0.2)
+    conv = lambda t, k: F.conv2d(t, p[f"{k}.conv.weight"], stride=2, padding=1)
+    up = lambda t, k: F.conv_transpose2d(t, p[f"{k}.up.weight"], bias=p.get(f"{k}.up.bias"), stride=2, padding=1)
+    d1 = lrelu(conv(x, "conv1"))                       # conv1: no activation, no BN; conv2's in-place LeakyReLU then rewrites it
+    d2 = lrelu(bn_train_noaffine(conv(d1, "conv2")))
+    d3 = lrelu(bn_train_noaffine(conv(d2, "conv3")))
+    d4 = lrelu(bn_train_noaffine(conv(d3, "conv4")))
+    d5 = conv(d4, "conv5")                             # no BN; consumed through upconv1's (out-of-place) ReLU only
+    u1 = torch.cat([bn_train_noaffine(up(F.relu(d5), "upconv1")), d4], 1)
+    u2 = torch.cat([bn_train_noaffine(up(F.relu(u1), "upconv2")), d3], 1)
+    u3 = torch.cat([bn_train_noaffine(up(F.relu(u2), "upconv3")), d2], 1)
+    u4 = torch.cat([bn_train_noaffine(up(F.relu(u3), "upconv4")), d1], 1)
+    return up(F.relu(u4), "upconv5")                   # bias, no BN
+
+
+def unet5ds_param_shapes(input_nc=3, output_nc=64, nf=64) -> dict:
+    """Reference state_dict names / shapes of UnetNoCond5DS parameters (ConvTranspose2d weights are [in, out, 4, 4])."""
+    s = {}
+    for k, (ci, co) in enumerate(((input_nc, nf), (nf, 2 * nf), (2 * nf, 4 * nf), (4 * nf, 8 * nf), (8 * nf, 8 * nf)), start=1):
+        s[f"conv{k}.conv.weight"] = (co, ci, 4, 4)
+    for k, (ci, co) in enumerate(((8 * nf, 8 * nf), (16 * nf, 4 * nf), (8 * nf, 2 * nf), (4 * nf, nf), (2 * nf, output_nc)), start=1):
+        s[f"upconv{k}.up.weight"] = (ci, co, 4, 4)
+    s["upconv5.up.bias"] = (output_nc,)
+    return s
+
+
+def seeded_unet_params(seed: int, input_nc=3, output_nc=64, nf=64, dtype=torch.float32) -> dict:
+    g = torch.Generator().manual_seed(seed)
+    p = {}
+    for name, shape in unet5ds_param_shapes(input_nc, output_nc, nf).items():
+        fan = (shape[1] if ".conv." in name else shape[0]) * 16 if len(shape) == 4 else 16 * 2 * nf
+        p[name] = ((torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan)).to(dtype)
+    return p

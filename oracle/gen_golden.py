@@ -26,7 +26,7 @@ from utils.graphics_utils import focal2fov, getProjectionMatrix, getWorld2View2 
 from utils.loss_utils import l1_loss_w, ssim              # noqa: E402  (reference)
 
 from gaussianavatar_b200 import synthetic as syn          # noqa: E402
-from oracle.avatar_oracle import seeded_pop_params        # noqa: E402
+from oracle.avatar_oracle import seeded_pop_params, seeded_unet_params        # noqa: E402
 
 
 def gen_test_pose_subset():
@@ -130,6 +130,26 @@ def gen_param_order():
     print("pop_param_order.json", len(order))
 
 
+def gen_unet():
+    """Stage-2 pose encoder: the reference's UnetNoCond5DS (model/modules.py:185-232) in training mode on a seeded input, with
+    seeded parameters (oracle.avatar_oracle.seeded_unet_params): output, input gradient and two weight gradients."""
+    from model.modules import UnetNoCond5DS                # reference
+    nf, cin, cout, side, B, seed = 8, 3, 8, 32, 2, 11
+    net = UnetNoCond5DS(input_nc=cin, output_nc=cout, nf=nf, up_mode="upconv", use_dropout=False)
+    missing, unexpected = net.load_state_dict(seeded_unet_params(seed, cin, cout, nf), strict=False)
+    assert not unexpected and all("running" in k or "num_batches" in k for k in missing), (missing, unexpected)
+    net.train()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, cin, side, side, generator=g).requires_grad_(True)
+    gout = torch.randn(B, cout, side, side, generator=g)
+    y = net(x.clone() if False else x)
+    (y * gout).sum().backward()
+    grads = dict(net.named_parameters())
+    np.savez_compressed(os.path.join(OUT, "unet5ds_nf8_s32.npz"), nf=nf, cin=cin, cout=cout, side=side, B=B, seed=seed,
+                        y=y.detach().numpy(), dx=x.grad.numpy(), d_conv3=grads["conv3.conv.weight"].grad.numpy(),
+                        d_upconv4=grads["upconv4.up.weight"].grad.numpy(), d_bias=grads["upconv5.up.bias"].grad.numpy(),
+                        bn2_running_mean=net.conv2.bn.running_mean.numpy())
+
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
@@ -139,5 +159,6 @@ if __name__ == "__main__":
     gen_losses()
     gen_camera()
     gen_param_order()
+    gen_unet()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

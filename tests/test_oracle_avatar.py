@@ -107,3 +107,23 @@ def test_tpose_identity_property():
                                a.query_lbs[None], C, iteration=2000)
     expect = a.query_points + (res[0].t() * 0.02)[a.valid_idx]
     assert (out["means3D"][0] - expect).abs().max() < 1e-5
+
+
+def test_unet5ds_oracle_matches_reference_fixture():
+    """Stage-2 pose encoder (next scope row): the restatement of UnetNoCond5DS -- including the in-place LeakyReLU that rewrites
+    the skip tensors -- against outputs / gradients of the reference module (oracle/gen_golden.py: gen_unet)."""
+    from oracle import avatar_oracle as ao
+    d = np.load(os.path.join(GOLD, "unet5ds_nf8_s32.npz"))
+    nf, cin, cout, side, B, seed = (int(d[k]) for k in ("nf", "cin", "cout", "side", "B", "seed"))
+    p = {k: v.requires_grad_(True) for k, v in ao.seeded_unet_params(seed, cin, cout, nf).items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, cin, side, side, generator=g).requires_grad_(True)
+    gout = torch.randn(B, cout, side, side, generator=g)
+    y = ao.unet5ds_forward(p, x)
+    assert np.abs(y.detach().numpy() - d["y"]).max() < 2e-5
+    (y * gout).sum().backward()
+    rel = lambda a, b: np.linalg.norm(a - b) / np.linalg.norm(b)
+    assert rel(x.grad.numpy(), d["dx"]) < 1e-4
+    assert rel(p["conv3.conv.weight"].grad.numpy(), d["d_conv3"]) < 1e-4
+    assert rel(p["upconv4.up.weight"].grad.numpy(), d["d_upconv4"]) < 1e-4
+    assert rel(p["upconv5.up.bias"].grad.numpy(), d["d_bias"]) < 1e-4
