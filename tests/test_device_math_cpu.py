@@ -1,4 +1,6 @@
-"""CPU: the sub-tile culling of the compositing kernels must be CONSERVATIVE -- a (Gaussian, sub-tile) pair may only be skipped when
+"""CPU checks of device-side math lifted from the product sources and compiled for the host (no GPU needed).
+
+1. The sub-tile culling of the compositing kernels must be CONSERVATIVE -- a (Gaussian, sub-tile) pair may only be skipped when
 every pixel of the sub-tile would have been skipped by the exact per-pixel test (alpha < 1/255 or power > 0) anyway; that is what makes
 the culled kernels bit-identical to the un-culled algorithm.  The test lifts the source text of `cull_radius2` / `rect_dist2` out of
 csrc/raster.cu, compiles it for the host and brute-forces random conics, opacities and rectangles (including extreme anisotropy)."""
@@ -79,3 +81,55 @@ def test_subtile_culling_is_conservative(tmp_path):
         evaluated, culled, violations = (int(v) for v in out)
         assert evaluated > 1_000_000 and culled > 100_000, (evaluated, culled)   # the test really exercises the cull branch
         assert violations == 0, f"{violations} pixels of culled pairs would have been blended"
+
+
+LAYOUT_HARNESS = r"""
+#include <cstdio>
+#include <cstdint>
+#include <set>
+#define __device__
+#define __forceinline__ inline
+%(functions)s
+// decoded on the device (profiles/r1_umma_mn_major_probe.md): byte offset of element (k, m) of an MN-major kind::tf32 operand
+static uint32_t probe_byte(int k, int m, uint32_t lbo, uint32_t sbo)
+{ return (uint32_t)(m / 32) * lbo + (uint32_t)(k / 4) * sbo + (uint32_t)(k %% 4) * 128u + (uint32_t)((((m %% 32) / 8) ^ (k %% 4)) * 32) + (uint32_t)(m %% 8) * 4u; }
+int main()
+{
+    int bad = 0;
+    std::set<uint32_t> seen;
+    for (int r = 0; r < 32; ++r)                 // r = K index (pixel) inside a 32-row chunk, v = 16-byte unit = channels 4v..4v+3
+        for (int v = 0; v < 8; ++v) {
+            const uint32_t off = mn_unit(r, v);
+            bad += off != probe_byte(r, 4 * v, 4096, 512);          // SBO = 512: 4-row atoms are contiguous, so row r sits at r * 128
+            bad += (off %% 16) != 0 || off >= 4096;
+            seen.insert(off);
+        }
+    bad += seen.size() != 256;                   // a bijection onto the chunk's 256 sixteen-byte slots
+    seen.clear();
+    for (int r = 0; r < 128; ++r)                // K-major 128-byte swizzle: 16-byte unit u of row r
+        for (int u = 0; u < 8; ++u) {
+            const uint32_t off = sw128_offset(r, u);
+            bad += off != (uint32_t)r * 128u + (uint32_t)((u ^ (r & 7)) << 4);
+            seen.insert(off);
+        }
+    bad += seen.size() != 1024;
+    std::printf("%%d\n", bad);
+    return 0;
+}
+"""
+
+
+def test_umma_layout_helpers_match_the_decoded_hardware_layout(tmp_path):
+    """`mn_unit` (conv_tc.cu) and `sw128_offset` (tc_common.cuh), lifted from the product sources and compiled for the host: the
+    MN-major helper must reproduce the layout decoded on the device word by word, and both must be bijections onto their tiles."""
+    conv = open(os.path.join(ROOT, "gaussianavatar_b200", "csrc", "conv_tc.cu")).read()
+    tcc = open(os.path.join(ROOT, "gaussianavatar_b200", "csrc", "tc_common.cuh")).read()
+    f1 = re.search(r"__device__ __forceinline__ uint32_t mn_unit\(.*?\}\n", conv, re.S)
+    f2 = re.search(r"__device__ __forceinline__ uint32_t sw128_offset\(.*?\}\n", tcc, re.S)
+    assert f1 and f2
+    cpp, exe = tmp_path / "layout.cpp", tmp_path / "layout"
+    cpp.write_text(LAYOUT_HARNESS % {"functions": f1.group(0) + "\n" + f2.group(0)})
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++17", "-O1", "-o", str(exe), str(cpp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout.strip() == "0"
