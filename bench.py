@@ -356,9 +356,16 @@ def main():
     mlp_ms = kms("mlp_tc_fwd", "mlp_tc_bwd") + sum(v[1] for k, v in per_step.items() if k.startswith("mlp_") and not k.startswith("mlp_tc"))
     dominant = max(per_step.items(), key=lambda kv: kv[1][1])[0] if per_step else None
 
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch (a 128 -> 128 layer at config-3 size) from the committed `ncu --set full`
-    # captures (profiles/r1_tc_bwd_ncu.md, profiles/r1_tc_fwd_ncu.md); the same launch's algorithmic bytes are 4 (bwd) / 2 (fwd) planes
-    ncu_traffic = {"mlp_tc_bwd": (402.866e6 + 111.877e6, 4 * plane), "mlp_tc_fwd": (134.399e6 + 84.248e6, 2 * plane)} if (wl.S, wl.side) == (512, 1024) else {}
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from committed `ncu --set full` captures: profiles/ncu_traffic.json names
+    # the kernel source hash each capture was taken at; a capture whose source has changed since is stale and reported as null
+    ncu_traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and (wl.S, wl.side) == (512, 1024):
+        import hashlib
+        for kname, rec in json.load(open(tpath)).get("kernels", {}).items():
+            src = os.path.join(ROOT, rec["source"])
+            if os.path.exists(src) and hashlib.sha256(open(src, "rb").read()).hexdigest() == rec["source_sha256"]:
+                ncu_traffic[kname] = (rec["dram_bytes"], rec["algorithmic_bytes"], rec["profile"])
 
     def hbm_roof(name, nbytes, label):
         ms = kms(name)
@@ -367,7 +374,8 @@ def main():
         tr = ncu_traffic.get(name)
         return {"kernel": label, "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": gbs / peaks["hbm_gbs"] if gbs else None, "traffic": tr[0] if tr else None,
-                "traffic_note": (f"ncu dram bytes of one 128->128 layer launch; algorithmic bytes of that launch: {tr[1]:.0f}" if tr else None),
+                "traffic_note": (f"ncu dram bytes of one 128->128 layer launch ({tr[2]}); algorithmic bytes of that launch: {tr[1]:.0f}" if tr
+                                 else "no ncu capture of the current kernel source committed (profiles/ncu_traffic.json)"),
                 "launches_per_step": n, "ms_per_step": ms,
                 "avg_launch_ms": ms / n if n else None, "algorithmic_bytes_per_step": nbytes,
                 "share_of_kernel_time": ms / total_kernel_ms if total_kernel_ms else None, "peak_source": peaks["_source"]}

@@ -266,6 +266,7 @@ class AvatarModel:
         offset_loss = torch.mean((dec[:, :3] * 0.02) ** 2)
         geo_loss = torch.mean(self.geo_feature ** 2)
         scale_loss = torch.mean(scales)
+        self._last_gaussians = (means, scales, colors)      # parity tests read the rasterizer's inputs / their gradients here
         images = self._render_frames(batch_data, means, scales, colors)
         return images, means, offset_loss, geo_loss, scale_loss
 

@@ -61,9 +61,12 @@ def test_fused_adam_matches_torch_adam():
     assert oa.state_dict()["state"][0]["exp_avg"].shape == ob.state_dict()["state"][0]["exp_avg"].shape
 
 
-def test_train_step_gradients_vs_oracle_chain():
+@pytest.mark.parametrize("mode", ["fp32", pytest.param("tf32", marks=pytest.mark.tf32)])
+def test_train_step_gradients_vs_oracle_chain(mode):
     """d loss / d (net params, geo_feature, pose, transl) of one stage-1 step: CUDA chain vs the CPU oracle chain
-    (torch autograd for the net / SMPL / LBS / losses + the C oracle's rasterizer backward)."""
+    (torch autograd for the net / SMPL / LBS / losses + the C oracle's rasterizer backward).  Runs on the strict-FP32 decoder
+    path (tight tolerance) and on the production tcgen05 TF32 path (the tolerance SURVEY.md App. C assigns to TF32)."""
+    tol = 5e-3 if mode == "fp32" else 3e-2
     from gaussianavatar_b200.trainer import Stage1Trainer
     from gaussianavatar_b200.workload import Stage1Workload
     from oracle import raster_oracle as ro
@@ -72,6 +75,7 @@ def test_train_step_gradients_vs_oracle_chain():
     with torch.no_grad():
         sd = wl.model.net.state_dict(); sd["decoder.conv8N.bias"] = torch.tensor([-3.9]); wl.model.net.load_state_dict(sd, strict=False)
     wl.make_ground_truth()
+    assert wl.model.net.tensor_cores == (mode == "tf32")
     tr = Stage1Trainer(wl.model)
     ids = [4, 5]
     batch = wl.device_batch(ids)
@@ -109,21 +113,21 @@ def test_train_step_gradients_vs_oracle_chain():
     reg = 3e-2 * o["scale_loss"] + 10.0 * o["offset_loss"] + o["geo_loss"]
     ref_loss = li.item() + reg.item()
     torch.autograd.backward([o["means3D"], o["colors"], o["scales"], reg], [torch.stack(gm), torch.stack(gc), torch.stack(gs), torch.ones(())])
-    assert abs(loss.item() - ref_loss) < 2e-5 * max(1.0, abs(ref_loss))
+    assert abs(loss.item() - ref_loss) < (2e-5 if mode == "fp32" else 2e-3) * max(1.0, abs(ref_loss))
     got = {k: v.cpu() for k, v in m.net.reference_grads().items()}
     worst = 0.0
     for k, v in p.items():
         if k.endswith(".bias") and ".bn" not in k and "conv8" not in k:
             continue                                     # exactly-zero gradients (bias in front of BatchNorm)
         worst = max(worst, _rel(got[k].numpy(), v.grad.numpy()))
-    assert worst < 5e-3, worst
-    assert _rel(m.geo_feature.grad.cpu().numpy(), geo.grad.numpy()) < 5e-3
+    assert worst < tol, worst
+    assert _rel(m.geo_feature.grad.cpu().numpy(), geo.grad.numpy()) < tol
     pg = m.pose.weight.grad.coalesce()
     dense = torch.zeros_like(m.pose.weight).index_add_(0, pg.indices()[0], pg.values()).cpu()
-    assert _rel(dense[ids].numpy(), pose.grad.numpy()) < 5e-3
+    assert _rel(dense[ids].numpy(), pose.grad.numpy()) < tol
     tg = m.transl.weight.grad.coalesce()
     dense_t = torch.zeros_like(m.transl.weight).index_add_(0, tg.indices()[0], tg.values()).cpu()
-    assert _rel(dense_t[ids].numpy(), transl.grad.numpy()) < 5e-3
+    assert _rel(dense_t[ids].numpy(), transl.grad.numpy()) < tol
     # and an optimizer step moves the parameters by Adam's first-step rule: |delta| == lr (sign of the gradient)
     before = m.net.flat.detach().clone()
     tr.sync_gradients(); m.optimizer.grad_scale = 1.0; m.step(1)
