@@ -305,9 +305,9 @@ def main():
         clocks.start()                     # nvidia-smi needs ~1 s to start sampling: begin before the warm-up steps
     run_value(args.warmup, 0)
     clocks.rows.clear()                    # keep only samples taken during the timed region
-    l0 = _lib.launch_count()
+    l0 = _lib.launch_count() + trainer.replayed_launches
     ms_value = timed(run_value, args.steps, args.warmup)
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() + trainer.replayed_launches - l0      # eager launches + the kernels inside the replayed step graphs
     clk = clocks.stop() if rank == 0 else {}
     fps = world * B * args.steps / (ms_value * 1e-3)
 
@@ -320,12 +320,16 @@ def main():
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps}
 
     # ---- per-kernel CUDA-event pass (same steps again, rank-local) -> roofline ---------------------------------------
+    trainer.finish()
+    graph_mode, trainer.use_graph = trainer.use_graph, False      # per-kernel events need eager launches (a replayed graph carries none)
     _lib.profile(True)
     _lib.profile_report()
     nprof = min(args.steps, 5)
     run_value(nprof, 2 * args.warmup + 2 * args.steps + 4)
+    trainer.finish()
     prof = _lib.profile_report()
     _lib.profile(False)
+    trainer.use_graph = graph_mode
     per_step = {k: (n / nprof, ms / nprof) for k, (n, ms) in prof.items()}
     total_kernel_ms = sum(ms for _, ms in per_step.values())
 
@@ -391,8 +395,7 @@ def main():
                     "peak_source": peaks["_source"] + "; tf32 dense = 1/2 x bf16 sustained", "ms_per_step": mlp_ms,
                     "share_of_kernel_time": mlp_ms / total_kernel_ms if total_kernel_ms else None}
     fwd_roofline = hbm_roof("mlp_tc_fwd", tc_fwd_bytes, "tc_fwd_kernel (one decoder layer forward, tcgen05 TF32): all launches of one step")
-    raster_fwd_names = ["preprocess_fwd_kernel", "cub_inclusive_sum", "duplicate_with_keys_kernel", "cub_radix_sort_pairs",
-                        "tile_ranges_kernel", "render_fwd_kernel"]
+    raster_fwd_names = ["preprocess_fwd_kernel", "tile_scan_kernel", "bucket_scatter_kernel", "tile_sort_kernel", "render_fwd_kernel"]
     raster_fwd_ms = kms(*raster_fwd_names) / B          # per frame
     raster_bwd_ms = kms("render_bwd_kernel", "preprocess_bwd_kernel") / B
     raster_gbs = cost["raster_fwd_bytes"] / (raster_fwd_ms * 1e-3) / 1e9 if raster_fwd_ms > 0 else None
@@ -420,7 +423,8 @@ def main():
                 "config": {"workload": f"config{args.config}: {wl.N} Gaussians, UV {wl.S}^2, {wl.side}x{wl.side}, stage-1 train step (feature net + "
                                        f"L1/SSIM), {B} frames/GPU/step, global batch {B * world}", "poses": wl.pose_source,
                            "l2_policy": "inputs and activations (>1.5 GB/step) exceed the 126 MB L2; no explicit flush",
-                           "parallelism": f"dp{world} (frames sharded, 1 all-reduce of 1.56M fp32 grads)"},
+                           "parallelism": f"dp{world} (frames sharded, 1 all-reduce of 1.56M fp32 grads)",
+                           "step_graph": bool(trainer.use_graph and trainer._graphs)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "mlp_fwd_roofline": fwd_roofline, "raster_roofline": raster_roofline,
                 "cpu_baseline": cpu_baseline,
                 "kernel_ms_per_step": {k: round(v[1], 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1][1])},

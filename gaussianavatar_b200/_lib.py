@@ -22,10 +22,15 @@ class GaRasterSettings(ctypes.Structure):
                 ("tanfovx", ctypes.c_float), ("tanfovy", ctypes.c_float), ("scale_modifier", ctypes.c_float)]
 
 
+class GaRasterBatchDesc(ctypes.Structure):
+    _fields_ = [("B", ctypes.c_int32), ("P", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32),
+                ("capacity", ctypes.c_int64), ("rot_stride", ctypes.c_int64), ("opac_stride", ctypes.c_int64),
+                ("scale_modifier", ctypes.c_float)]
+
+
 class GaRasterViews(ctypes.Structure):
-    _fields_ = [(n, c_vp) for n in ("depth", "xy", "conic_opacity", "cov3d", "tiles_touched", "offsets", "rect",
-                                    "keys_unsorted", "keys_sorted", "vals_unsorted", "vals_sorted", "ranges", "final_T",
-                                    "n_contrib")]
+    _fields_ = [(n, c_vp) for n in ("depth", "xy", "conic_opacity", "cov3d", "tiles_touched", "rect", "point_list", "ranges",
+                                    "tile_count", "final_T", "n_contrib", "status")]
 
 
 class GaDecoderDesc(ctypes.Structure):
@@ -54,7 +59,7 @@ _SIGNATURES = {
     "ga_raster_img_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
     "ga_raster_binning_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
     "ga_raster_bwd_scratch_bytes": (ctypes.c_size_t, [ctypes.c_int32]),
-    "ga_raster_forward_preprocess": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings)] + [c_vp] * 8 + [ctypes.POINTER(ctypes.c_int64), c_vp]),
+    "ga_raster_forward_preprocess": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings)] + [c_vp] * 9 + [ctypes.POINTER(ctypes.c_int64), c_vp]),
     "ga_raster_forward_render": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings), c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_int64, c_vp, c_vp, c_vp]),
     "ga_raster_backward": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings)] + [c_vp] * 11 + [ctypes.c_int64] + [c_vp] * 9),
     "ga_smpl_forward": (ctypes.c_int, [ctypes.c_int32] + [c_vp] * 7),
@@ -69,12 +74,21 @@ _SIGNATURES = {
     "ga_loss_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 3),
     "ga_loss_forward": (ctypes.c_int, [ctypes.c_int32] * 3 + [c_vp, c_vp, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp]),
     "ga_loss_backward": (ctypes.c_int, [ctypes.c_int32] * 3 + [c_vp, c_vp, ctypes.c_float, ctypes.c_float, c_vp, c_vp, c_vp, c_vp]),
-    "ga_adam_step": (ctypes.c_int, [ctypes.c_int64, c_vp, c_vp, c_vp, c_vp] + [ctypes.c_float] * 4 + [ctypes.c_int64, ctypes.c_float, c_vp]),
+    "ga_adam_step": (ctypes.c_int, [ctypes.c_int64, c_vp, c_vp, c_vp, c_vp] + [ctypes.c_float] * 4 + [ctypes.c_int64, ctypes.c_float, c_vp, c_vp]),
+    "ga_adam_step_dev": (ctypes.c_int, [ctypes.c_int64] + [c_vp] * 7),
     "ga_tc_linear_forward": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_vp, ctypes.c_int32, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp, c_vp,
                                             ctypes.c_int32, ctypes.c_int32, c_vp, c_vp, c_vp]),
     "ga_tc_linear_backward": (ctypes.c_int, [ctypes.c_int32, c_vp, c_vp, ctypes.c_int32, c_vp, c_vp, ctypes.c_int32, c_vp, c_vp, ctypes.c_int32, c_vp,
                                              ctypes.c_int32, c_vp, ctypes.c_int32, ctypes.c_int32, c_vp, c_vp, c_vp]),
-    "ga_raster_views": (ctypes.c_int, [ctypes.POINTER(GaRasterSettings), c_vp, c_vp, c_vp, ctypes.c_int64, ctypes.POINTER(GaRasterViews)]),
+    "ga_raster_views": (ctypes.c_int, [ctypes.c_int32] * 4 + [ctypes.c_int64, c_vp, c_vp, c_vp, ctypes.POINTER(GaRasterViews)]),
+    "ga_rasterb_geom_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 2),
+    "ga_rasterb_img_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 3),
+    "ga_rasterb_binning_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 3 + [ctypes.c_int64]),
+    "ga_rasterb_bwd_scratch_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 2),
+    "ga_rasterb_status": (c_vp, [ctypes.c_int32] * 3 + [c_vp]),
+    "ga_rasterb_status_to_host": (ctypes.c_int, [ctypes.c_int32] * 3 + [c_vp] * 4),
+    "ga_rasterb_forward": (ctypes.c_int, [ctypes.POINTER(GaRasterBatchDesc)] + [c_vp] * 13),
+    "ga_rasterb_backward": (ctypes.c_int, [ctypes.POINTER(GaRasterBatchDesc)] + [c_vp] * 19),
     "ga_tc_conv5x5": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp]),
     "ga_round_tf32": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_vp]),
 }

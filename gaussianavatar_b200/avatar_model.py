@@ -212,8 +212,11 @@ class AvatarModel:
     # ------------------------------------------------------------------------------------------------------------------
     def _posed_gaussians(self, idx, iteration, ramp=True):
         """SMPL -> cano2live -> net (once) -> fused LBS/assembly.  Returns means3D, scales, colors [B,N,3] and dec_out."""
-        pose_batch = self.pose(idx)
-        transl_batch = self.transl(idx)
+        if getattr(self, "_detach_pose", False):      # pose optimisation inactive (epoch <= pose_op_start_iter): its gradients are never read
+            pose_batch, transl_batch = self.pose.weight.detach()[idx], self.transl.weight.detach()[idx]
+        else:
+            pose_batch = self.pose(idx)
+            transl_batch = self.transl(idx)
         B = pose_batch.shape[0]
         cano2live = SmplCano2Live.apply(pose_batch, transl_batch, self._rest_joints, self._inv_cano)     # [B,24,12]
         S = int(self.model_parms.query_posmap_size)
@@ -230,7 +233,76 @@ class AvatarModel:
                             full_proj_transform=batch_data["full_proj_transform"][b], active_sh_degree=0,
                             camera_center=batch_data["camera_center"][b])
 
+    # ---- batched rasterization: every frame of the step in one set of launches, no host read-back -------------------------------
+    @staticmethod
+    def _scalar_list(v, B):
+        """Per-frame python numbers of a batch field (a list, or a CPU / CUDA tensor after the reference's collate + to_cuda)."""
+        if torch.is_tensor(v):
+            return v.reshape(-1)[:B].tolist()          # a CUDA tensor costs one host sync (the reference's own loop reads them too)
+        return [float(x) for x in list(v)[:B]]
+
+    def _batch_cameras(self, batch_data, B, dev):
+        """[B,40] camera block for ga_rasterb_* (view, proj, tan(Fov/2)); the tangent pair is cached per Fov tuple."""
+        import math
+        from .rasterizer import CAM_STRIDE
+        fx, fy = batch_data["FovX"], batch_data["FovY"]
+        if torch.is_tensor(fx) and fx.is_cuda:
+            tans = torch.stack([torch.tan(fx.double() * 0.5), torch.tan(fy.double() * 0.5)], 1).float()
+        else:
+            key = (tuple(self._scalar_list(fx, B)), tuple(self._scalar_list(fy, B)))
+            cache = self.__dict__.setdefault("_tan_cache", {})
+            tans = cache.get(key)
+            if tans is None:
+                tans = torch.tensor([[math.tan(a * 0.5), math.tan(b * 0.5)] for a, b in zip(*key)], dtype=torch.float32).to(dev)
+                if len(cache) < 64:
+                    cache[key] = tans
+        cams = torch.zeros(B, CAM_STRIDE, dtype=torch.float32, device=dev)
+        view, proj = batch_data["world_view_transform"], batch_data["full_proj_transform"]
+        if not torch.is_tensor(view):
+            view, proj = torch.stack(list(view)[:B]), torch.stack(list(proj)[:B])
+        cams[:, 0:16] = view.reshape(B, 16)
+        cams[:, 16:32] = proj.reshape(B, 16)
+        cams[:, 32:34] = tans
+        return cams
+
+    def raster_plan(self, B, P, H, W):
+        from .rasterizer import RasterBatchPlan
+        plans = self.__dict__.setdefault("_raster_plans", {})
+        key = (int(B), int(P), int(H), int(W))
+        if key not in plans:
+            plans[key] = RasterBatchPlan(B, P, H, W, self.device)
+        return plans[key]
+
+    def raster_ok(self, wait=True) -> bool:
+        """False if the last batched render overflowed its binning buffer (the buffer has then been grown: run it again)."""
+        plan = getattr(self, "_last_plan", None)
+        return True if plan is None else plan.check(wait)
+
+    def _render_batched(self, batch_data, means, scales, colors):
+        from .rasterizer import rasterize_batch
+        B, P = int(means.shape[0]), int(means.shape[1])
+        H, W = int(self._scalar_list(batch_data["height"], 1)[0]), int(self._scalar_list(batch_data["width"], 1)[0])
+        cams = batch_data["_cams"] if "_cams" in batch_data else self._batch_cameras(batch_data, B, means.device)
+        plan = self.raster_plan(B, P, H, W)
+        self._last_plan = plan
+        images = rasterize_batch(means, colors, scales, self.fix_rotation, self.fix_opacity, cams, self.background, plan)
+        if not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing() and not plan.check(wait=True):   # inference: make the result right before returning it
+            images = rasterize_batch(means, colors, scales, self.fix_rotation, self.fix_opacity, cams, self.background, plan)
+            if not plan.check(wait=True):
+                raise RuntimeError("batched rasterizer: binning buffer overflowed twice in a row")
+        return images
+
+    def _uniform_frames(self, batch_data, B):
+        h, w = self._scalar_list(batch_data["height"], B), self._scalar_list(batch_data["width"], B)
+        return len(set(h)) == 1 and len(set(w)) == 1
+
     def _render_frames(self, batch_data, means, scales, colors):
+        if (means.is_cuda and means.shape[0] <= 8 and os.environ.get("GA_RASTER_BATCHED", "1") != "0"
+                and self._uniform_frames(batch_data, means.shape[0])):
+            return self._render_batched(batch_data, means, scales, colors)
+        return self._render_frames_one_by_one(batch_data, means, scales, colors)
+
+    def _render_frames_one_by_one(self, batch_data, means, scales, colors):
         """The reference rasterizes the frames of a batch one after the other (avatar_model.py:332-365).  Frames are independent, and
         the compositing kernels end in a long tail of a few crowded tiles, so consecutive frames go to two alternating side
         streams: frame b+1's preprocess / sort (and, in the backward, its replay) fill the SMs frame b's tail leaves idle.

@@ -24,6 +24,18 @@ void set_error(const char *fmt, ...)
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int num_sms()
+{
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : kNumSMs;
+    }
+    return cached[dev];
+}
+
 // ---- per-kernel event timing ----------------------------------------------------------------------------------------
 namespace {
 struct ProfRec { const char *name; cudaEvent_t a, b; };

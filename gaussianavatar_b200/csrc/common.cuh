@@ -67,7 +67,8 @@ struct Carver {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (compile-time grid constants of the tensor-core kernels)
+int num_sms();                // multiProcessorCount of the current device, queried once per device
 
 // 16-byte vector reduction to global memory (sm_90+): one L2 atomic for four consecutive floats (16-byte aligned address)
 __device__ __forceinline__ void red_add_v4(float *addr, float a, float b, float c, float d)

@@ -160,14 +160,17 @@ __global__ void loss_coef_kernel(const float *__restrict__ g, float w_l1, float 
     coef[1] = -gv * w_ssim * inv_n;
 }
 
-bool g_gauss_ready = false;
+bool g_gauss_ready[64] = {};      // __constant__ memory is per device: one flag per device ordinal
 int ensure_gauss()
 {
-    if (g_gauss_ready) return GA_OK;
+    int dev = 0;
+    GA_CHECK_CUDA(cudaGetDevice(&dev));
+    GA_REQUIRE(dev >= 0 && dev < 64, "device ordinal %d out of range", dev);
+    if (g_gauss_ready[dev]) return GA_OK;
     float g[kWin];
     gauss_host(g);
     GA_CHECK_CUDA(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
-    g_gauss_ready = true;
+    g_gauss_ready[dev] = true;
     return GA_OK;
 }
 
@@ -228,12 +231,18 @@ extern "C" int ga_loss_backward(int32_t B, int32_t H, int32_t W, const float *im
 // ---------------------------------------------------------------------------------------------------------------------
 namespace ga {
 namespace {
+// hyper (device, optional): [lr, beta1, beta2, eps, bias_correction1, sqrt(bias_correction2), grad_scale] — read at run time so
+// that a captured CUDA graph does not freeze the schedule; skip (device, optional): a non-zero word turns the launch into a
+// no-op (the batched rasterizer's overflow flag: a step whose binning buffer overflowed must not be committed).
 __global__ void __launch_bounds__(256)
 adam_kernel(size_t n, float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, float lr,
-            float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float grad_scale)
+            float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float grad_scale, const float *__restrict__ hyper,
+            const int32_t *__restrict__ skip)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (skip && *skip != 0) return;
+    if (hyper) { lr = hyper[0]; beta1 = hyper[1]; beta2 = hyper[2]; eps = hyper[3]; bc1 = hyper[4]; bc2_sqrt = hyper[5]; grad_scale = hyper[6]; }
     const float gr = g[i] * grad_scale;
     const float mi = beta1 * m[i] + (1.f - beta1) * gr;       // exp_avg.lerp_(grad, 1 - beta1)
     const float vi = beta2 * v[i] + (1.f - beta2) * gr * gr;  // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
@@ -245,14 +254,26 @@ adam_kernel(size_t n, float *__restrict__ p, const float *__restrict__ g, float 
 }  // namespace ga
 
 extern "C" int ga_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float lr, float beta1,
-                            float beta2, float eps, int64_t step, float grad_scale, void *stream_)
+                            float beta2, float eps, int64_t step, float grad_scale, const int32_t *skip_flag, void *stream_)
 {
     GA_REQUIRE(n >= 0 && step >= 1, "bad adam args n=%lld step=%lld", (long long)n, (long long)step);
     if (n == 0) return GA_OK;
     GA_REQUIRE(param && grad && exp_avg && exp_avg_sq, "NULL pointer argument");
     const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
     { ProfScope _ps("adam_kernel", static_cast<cudaStream_t>(stream_)); adam_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>((size_t)n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps,
-                                                                             (float)bc1, (float)sqrt(bc2), grad_scale); }
+                                                                             (float)bc1, (float)sqrt(bc2), grad_scale, nullptr, skip_flag); }
+    GA_CHECK_LAUNCH("adam_kernel");
+    return GA_OK;
+}
+
+extern "C" int ga_adam_step_dev(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, const float *hyper7,
+                                const int32_t *skip_flag, void *stream_)
+{
+    GA_REQUIRE(n >= 0, "bad adam args n=%lld", (long long)n);
+    if (n == 0) return GA_OK;
+    GA_REQUIRE(param && grad && exp_avg && exp_avg_sq && hyper7, "NULL pointer argument");
+    { ProfScope _ps("adam_kernel", static_cast<cudaStream_t>(stream_)); adam_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream_)>>>((size_t)n, param, grad, exp_avg, exp_avg_sq, 0.f, 0.f, 0.f, 0.f,
+                                                                             1.f, 1.f, 1.f, hyper7, skip_flag); }
     GA_CHECK_LAUNCH("adam_kernel");
     return GA_OK;
 }

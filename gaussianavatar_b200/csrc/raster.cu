@@ -1,13 +1,29 @@
-// Differentiable 3D-Gaussian tile rasterizer for sm_100a — forward (K1..K6) and backward (K7, fused K8/K9).
+// Differentiable 3D-Gaussian tile rasterizer for sm_100a — forward (K1..K6) and backward (K7, fused K8/K9), for one frame or
+// for all frames of a training step in one set of launches.
 //
 // Replaces what the reference reaches through `GaussianRasterizer(raster_settings)(...)`
 // (/root/reference gaussian_renderer/__init__.py:36-48; [UPSTREAM] diff-gaussian-rasterization, not vendored).
 // Algorithm and constants: SURVEY.md §8 "a-8 forward spec" / "a-9 backward spec".  Written from that specification,
-// not from upstream source.
+// not from upstream source.  The RESULTS are upstream's (tile ranges, depth-ordered per-tile lists, image, gradients);
+// the way they are produced is not:
+//
+//   binning   upstream: duplicateWithKeys -> global 64-bit radix sort of all (tile | depth) keys -> identifyTileRanges, with a
+//             device->host read of the instance count in the middle.  Here: K1 counts instances per tile, ONE CTA scans the
+//             counts (tile ranges fall out directly), K3 scatters (depth bits | Gaussian index) into the tile's bucket and one
+//             CTA per tile sorts its bucket in shared memory.  The order inside a tile is upstream's (depth bits, then Gaussian
+//             index = the stable order of its key sort), no launch shape depends on the instance count, and nothing is read back
+//             by the host: the binning buffer has a caller-chosen capacity, an overflow raises a device-side flag
+//             (status[1]) and the affected tiles are skipped, never overrun.
+//   K6        one warp per 8x4-pixel sub-tile walks the tile list on its own (no CTA barriers): 32 entries are tested against
+//             the sub-tile in parallel and only the survivors are composited.  The sort kernel leaves packed per-instance
+//             records (centre, conic, opacity, colour, cull radius) in list order, so the walk streams instead of gathering.
+//             Every 256 list positions each pixel's (T, C) is checkpointed ...
+//   K7        ... so that the backward runs ONE CTA PER 256-ENTRY SEGMENT of a tile list, all segments in parallel, each
+//             starting from the checkpoint behind it (upstream replays a whole tile list serially in one CTA).
 //
 // Arithmetic contract: every value that feeds an INTEGER decision (depth key bits, radius, tile rect)
 // is computed with explicit round-to-nearest intrinsics in exactly the operation order of oracle/raster_oracle_impl.inc,
-// so keys / radii / ranges are bit-exact against the CPU oracle regardless of nvcc's FMA contraction.
+// so radii / ranges / list order are bit-exact against the CPU oracle regardless of nvcc's FMA contraction.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -17,6 +33,20 @@ namespace {
 
 constexpr int kTile = 16;
 constexpr int kBlock = kTile * kTile;
+constexpr int kSeg = 256;            // list positions per checkpoint interval = per backward work item
+constexpr int kSortThreads = 512;
+constexpr int kSortMax = 8192;       // keys one CTA sorts in shared memory at a time (64 KB)
+constexpr int kStatusInts = 16;      // status[0] instances, [1] overflow flag, [2] segments, [4+b] first instance of frame b
+
+struct Dims {
+    int B, P, H, W, gx, gy, T;
+};
+inline Dims make_dims(int B, int P, int H, int W)
+{
+    Dims d{B, P, H, W, cdiv(W, kTile), cdiv(H, kTile), 0};
+    d.T = d.gx * d.gy;
+    return d;
+}
 
 struct GeomViews {
     float *depth;
@@ -24,87 +54,83 @@ struct GeomViews {
     float4 *conic_o;
     float *cov3d;
     uint32_t *tiles;
-    uint32_t *offsets;
     ushort4 *rect;
-    void *scan_temp;
-    size_t scan_temp_bytes;
     size_t total;
 };
 
-size_t scan_temp_bytes_for(int P)
-{
-    size_t b = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, P);
-    return b;
-}
-
-GeomViews carve_geom(void *buf, int P)
+GeomViews carve_geom(void *buf, size_t BP)
 {
     Carver c(buf);
     GeomViews g;
-    const size_t n = P > 0 ? (size_t)P : 1;
+    const size_t n = BP > 0 ? BP : 1;
     g.depth = c.take<float>(n);
     g.xy = c.take<float2>(n);
     g.conic_o = c.take<float4>(n);
     g.cov3d = c.take<float>(6 * n);
     g.tiles = c.take<uint32_t>(n);
-    g.offsets = c.take<uint32_t>(n);
     g.rect = c.take<ushort4>(n);
-    g.scan_temp_bytes = scan_temp_bytes_for(P > 0 ? P : 1);
-    g.scan_temp = c.take<char>(g.scan_temp_bytes);
     g.total = c.used();
     return g;
 }
 
 struct ImgViews {
-    float *final_T;
-    uint32_t *n_contrib;
-    uint2 *ranges;
+    float *final_T;          // [B][H*W]
+    uint32_t *n_contrib;     // [B][H*W]
+    float4 *final_state;     // [B*T][256] tile-major (T, C0, C1, C2 without background)
+    uint2 *ranges;           // [B*T] global [start, end) into the instance arrays
+    uint32_t *count;         // [B*T] instances per tile (K1)
+    uint32_t *cursor;        // [B*T] scatter cursor (starts at ranges.x)
+    uint32_t *seg_start;     // [B*T+1] exclusive scan of ceil(count/256)
+    uint32_t *tile_maxc;     // [B*T] max n_contrib of the tile's pixels
+    uint32_t *order;         // [B*T] tiles by decreasing list length (classes of log2), empty tiles last
+    int32_t *status;         // [kStatusInts]
     size_t total;
 };
 
-ImgViews carve_img(void *buf, int H, int W)
+ImgViews carve_img(void *buf, const Dims &d)
 {
     Carver c(buf);
     ImgViews v;
-    const size_t hw = (size_t)H * W, T = (size_t)cdiv(W, kTile) * cdiv(H, kTile);
+    const size_t hw = (size_t)d.B * d.H * d.W, BT = (size_t)d.B * d.T;
     v.final_T = c.take<float>(hw ? hw : 1);
     v.n_contrib = c.take<uint32_t>(hw ? hw : 1);
-    v.ranges = c.take<uint2>(T ? T : 1);
+    v.final_state = c.take<float4>((BT ? BT : 1) * kBlock);
+    v.ranges = c.take<uint2>(BT ? BT : 1);
+    v.count = c.take<uint32_t>(BT ? BT : 1);
+    v.cursor = c.take<uint32_t>(BT ? BT : 1);
+    v.seg_start = c.take<uint32_t>(BT + 1);
+    v.tile_maxc = c.take<uint32_t>(BT ? BT : 1);
+    v.order = c.take<uint32_t>(BT ? BT : 1);
+    v.status = c.take<int32_t>(kStatusInts);
     v.total = c.used();
     return v;
 }
 
 struct BinViews {
-    uint64_t *keys_unsorted, *keys;
-    uint32_t *vals_unsorted, *vals;
-    void *sort_temp;
-    size_t sort_temp_bytes;
+    uint64_t *bucket;        // [cap] (depth bits << 32 | Gaussian index), grouped by tile, unsorted inside a tile
+    uint32_t *point_list;    // [cap] Gaussian index in upstream's sorted order
+    float4 *recA, *recB, *recC;   // [cap] packed records in list order: (x, y, cull r^2, idx) (conic xyz, opacity) (r, g, b, -)
+    float4 *ckpt;            // [max_segments][256] per-pixel (T, C) at the start of each 256-entry segment
+    uint32_t *seg_tile;      // [max_segments] segment -> tile
+    size_t max_segments;
     size_t total;
 };
 
-int sort_end_bit(int H, int W)
-{
-    const int T = cdiv(W, kTile) * cdiv(H, kTile);
-    int bits = 0;
-    while ((1 << bits) < T) ++bits;  // bits to represent tile ids 0..T-1
-    return 32 + (bits > 0 ? bits : 1);
-}
+inline size_t max_segments_for(int64_t cap, const Dims &d) { return (size_t)(cap / kSeg) + (size_t)d.B * d.T + 1; }
 
-BinViews carve_bin(void *buf, int64_t R, int H, int W)
+BinViews carve_bin(void *buf, int64_t cap, const Dims &d)
 {
     Carver c(buf);
     BinViews b;
-    const size_t n = R > 0 ? (size_t)R : 1;
-    b.keys_unsorted = c.take<uint64_t>(n);
-    b.keys = c.take<uint64_t>(n);
-    b.vals_unsorted = c.take<uint32_t>(n);
-    b.vals = c.take<uint32_t>(n);
-    size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
-                                    (uint32_t *)nullptr, (int)n, 0, sort_end_bit(H, W));
-    b.sort_temp_bytes = tb;
-    b.sort_temp = c.take<char>(tb);
+    const size_t n = cap > 0 ? (size_t)cap : 1;
+    b.max_segments = max_segments_for(cap, d);
+    b.bucket = c.take<uint64_t>(n);
+    b.point_list = c.take<uint32_t>(n);
+    b.recA = c.take<float4>(n);
+    b.recB = c.take<float4>(n);
+    b.recC = c.take<float4>(n);
+    b.ckpt = c.take<float4>(b.max_segments * kBlock);
+    b.seg_tile = c.take<uint32_t>(b.max_segments);
     b.total = c.used();
     return b;
 }
@@ -141,21 +167,36 @@ __device__ __forceinline__ void quat_to_rot(float qr, float qx, float qy, float 
     R[2][2] = sub_(1.f, mul_(2.f, add_(mul_(qx, qx), mul_(qy, qy))));
 }
 
-// K1: one thread per Gaussian.
+// Where a frame's camera comes from: a device array of kCamStride floats per frame (batched path: view 0..15, proj 16..31,
+// tanfovx 32, tanfovy 33) or two device matrices plus host scalars (per-frame API, stride 0).
+constexpr int kCamStride = 40;
+struct CamSrc {
+    const float *view, *proj, *tan;
+    int stride;
+    float tanx, tany;
+};
+
+// K1: one thread per Gaussian (blockIdx.y = frame).  Besides the per-Gaussian state it counts, per tile, the instances the
+// tile will receive (tile_count[frame][tile]): the binning that follows is a bucket sort by tile, not a global sort.
 __global__ void __launch_bounds__(256)
-preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, float tanfovx, float tanfovy, float mod,
-                      const float *__restrict__ means3D, const float *__restrict__ scales,
-                      const float *__restrict__ rots, const float *__restrict__ opac,
-                      const float *__restrict__ view_g, const float *__restrict__ proj_g, float *__restrict__ depth,
+preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, CamSrc cam, float mod, const float *__restrict__ means3D,
+                      const float *__restrict__ scales, const float *__restrict__ rots, long long rot_stride,
+                      const float *__restrict__ opac, long long opac_stride, float *__restrict__ depth,
                       float2 *__restrict__ xy, float4 *__restrict__ conic_o, float *__restrict__ cov3d,
-                      uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect, int32_t *__restrict__ radii)
+                      uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect, int32_t *__restrict__ radii,
+                      uint32_t *__restrict__ tile_count)
 {
+    const int b = blockIdx.y;
     __shared__ float view[16], proj[16];
-    if (threadIdx.x < 16) view[threadIdx.x] = view_g[threadIdx.x];
-    else if (threadIdx.x < 32) proj[threadIdx.x - 16] = proj_g[threadIdx.x - 16];
+    if (threadIdx.x < 16) view[threadIdx.x] = cam.view[(size_t)b * cam.stride + threadIdx.x];
+    else if (threadIdx.x < 32) proj[threadIdx.x - 16] = cam.proj[(size_t)b * cam.stride + threadIdx.x - 16];
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
+    const float tanfovx = cam.tan ? cam.tan[(size_t)b * cam.stride] : cam.tanx;
+    const float tanfovy = cam.tan ? cam.tan[(size_t)b * cam.stride + 1] : cam.tany;
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= P) return;
+    const size_t i = (size_t)b * P + il;
+    const float *rq = rots + (size_t)b * rot_stride + 4 * (size_t)il;
 
     radii[i] = 0;
     tiles[i] = 0;
@@ -176,7 +217,7 @@ preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, float tanfovx, float 
 
     const float sv[3] = {mul_(mod, scales[3 * (size_t)i]), mul_(mod, scales[3 * (size_t)i + 1]), mul_(mod, scales[3 * (size_t)i + 2])};
     float Rm[3][3];
-    quat_to_rot(rots[4 * (size_t)i], rots[4 * (size_t)i + 1], rots[4 * (size_t)i + 2], rots[4 * (size_t)i + 3], Rm);
+    quat_to_rot(rq[0], rq[1], rq[2], rq[3], Rm);
     float Mm[3][3];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -243,48 +284,92 @@ preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, float tanfovx, float 
     depth[i] = tvz;
     radii[i] = radius;
     xy[i] = make_float2(pixx, pixy);
-    conic_o[i] = make_float4(conx, cony, conz, opac[i]);
+    conic_o[i] = make_float4(conx, cony, conz, opac[(size_t)b * opac_stride + il]);
     tiles[i] = (uint32_t)area;
     rect[i] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx, (unsigned short)rmaxy);
+    uint32_t *tc = tile_count + (size_t)b * gx * gy;
+    for (int y = rminy; y < rmaxy; ++y)
+        for (int x = rminx; x < rmaxx; ++x) atomicAdd(&tc[y * gx + x], 1u);
 }
 
-// K3: one thread per Gaussian writes its (tile<<32 | depth bits, index) instances.
-__global__ void __launch_bounds__(256)
-duplicate_with_keys_kernel(int P, int gx, const float *__restrict__ depth, const uint32_t *__restrict__ offsets,
-                           const uint32_t *__restrict__ tiles, const ushort4 *__restrict__ rect,
-                           uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+// K2: ONE CTA scans the per-tile instance counts of all frames: tile ranges (global offsets into the instance arrays; untouched
+// tiles keep (0,0) as upstream's memset leaves them), the scatter cursors, the segment index space of the backward, the
+// per-frame base offsets and the overflow flag.  A tile whose range would end past the capacity gets an empty range (and the
+// flag is raised): nothing downstream can overrun the buffers.  It also orders the tiles by list length (classes of
+// floor(log2(count)), longest first; `order`, with status[3] = number of non-empty tiles) so that the per-tile kernels start
+// their longest work first and touch empty tiles last or not at all.
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int n, int T, long long capacity, const uint32_t *__restrict__ count, uint2 *__restrict__ ranges,
+                 uint32_t *__restrict__ cursor, uint32_t *__restrict__ seg_start, uint32_t *__restrict__ order,
+                 int32_t *__restrict__ status)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
+    using Scan = cub::BlockScan<unsigned long long, 1024>;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ unsigned long long carry_c, carry_s;
+    __shared__ uint32_t cls_count[33], cls_base[33];
+    if (threadIdx.x == 0) { carry_c = 0; carry_s = 0; }
+    if (threadIdx.x < 33) cls_count[threadIdx.x] = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long c = i < n ? count[i] : 0ull;
+        unsigned long long ex, tot;
+        Scan(tmp).ExclusiveSum(c, ex, tot);
+        const unsigned long long pos = carry_c + ex, end = pos + c;
+        const bool fits = end <= (unsigned long long)capacity;
+        const unsigned long long segs = (fits && c) ? (c + kSeg - 1) / kSeg : 0ull;
+        __syncthreads();
+        unsigned long long sex, stot;
+        Scan(tmp).ExclusiveSum(segs, sex, stot);
+        if (i < n) {
+            ranges[i] = (fits && c) ? make_uint2((uint32_t)pos, (uint32_t)end) : make_uint2(0u, 0u);
+            cursor[i] = (uint32_t)(pos < 0xffffffffull ? pos : 0xffffffffull);
+            seg_start[i] = (uint32_t)(carry_s + sex);
+            if (i % T == 0) status[4 + i / T] = (int32_t)(pos < 0x7fffffffull ? pos : 0x7fffffffull);
+            // class 0: empty (or not fitting) tiles, class k >= 1: 2^(k-1) <= count < 2^k
+            atomicAdd(&cls_count[(fits && c) ? 32 - __clz((uint32_t)c) : 0], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { carry_c += tot; carry_s += stot; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        status[0] = (int32_t)(carry_c < 0x7fffffffull ? carry_c : 0x7fffffffull);
+        status[1] = carry_c > (unsigned long long)capacity ? 1 : 0;
+        status[2] = (int32_t)carry_s;
+        status[4 + n / T] = status[0];
+        seg_start[n] = (uint32_t)carry_s;
+        uint32_t run = 0;
+        for (int k = 32; k >= 0; --k) { cls_base[k] = run; run += cls_count[k]; }    // longest class first, empties last
+        status[3] = (int32_t)cls_base[0];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const uint2 r = ranges[i];
+        const uint32_t c = r.y - r.x;
+        order[atomicAdd(&cls_base[c ? 32 - __clz(c) : 0], 1u)] = (uint32_t)i;
+    }
+}
+
+// K3: one thread per Gaussian drops (depth bits << 32 | index) into the bucket of every tile its rect touches.
+__global__ void __launch_bounds__(256)
+bucket_scatter_kernel(int P, int gx, int T, long long capacity, const float *__restrict__ depth,
+                      const uint32_t *__restrict__ tiles, const ushort4 *__restrict__ rect, uint32_t *__restrict__ cursor,
+                      uint64_t *__restrict__ bucket)
+{
+    const int b = blockIdx.y;
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= P) return;
+    const size_t i = (size_t)b * P + il;
     if (tiles[i] == 0) return;
-    uint32_t off = (i == 0) ? 0u : offsets[i - 1];
-    const uint32_t dbits = __float_as_uint(depth[i]);
+    const uint64_t key = ((uint64_t)__float_as_uint(depth[i]) << 32) | (uint32_t)il;
     const ushort4 r = rect[i];
+    uint32_t *cur = cursor + (size_t)b * T;
     for (int y = r.y; y < r.w; ++y)
         for (int x = r.x; x < r.z; ++x) {
-            const uint64_t key = ((uint64_t)(uint32_t)(y * gx + x) << 32) | dbits;
-            keys[off] = key;
-            vals[off] = (uint32_t)i;
-            ++off;
+            const uint32_t pos = atomicAdd(&cur[y * gx + x], 1u);
+            if ((long long)pos < capacity) bucket[pos] = key;
         }
-}
-
-// K5: [start,end) of every tile in the sorted list.
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(int64_t R, const uint64_t *__restrict__ keys, uint2 *__restrict__ ranges)
-{
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= R) return;
-    const uint32_t t = (uint32_t)(keys[k] >> 32);
-    if (k == 0) ranges[t].x = 0;
-    else {
-        const uint32_t pt = (uint32_t)(keys[k - 1] >> 32);
-        if (pt != t) {
-            ranges[pt].y = (uint32_t)k;
-            ranges[t].x = (uint32_t)k;
-        }
-    }
-    if (k == R - 1) ranges[t].y = (uint32_t)R;
 }
 
 // Squared distance from a Gaussian's centre beyond which it is certain that the compositing loop skips it
@@ -311,98 +396,202 @@ __device__ __forceinline__ float rect_dist2(const float2 c, float x0, float x1, 
     return ex * ex + ey * ey;
 }
 
-// K6: one CTA per 16x16 tile, one thread per pixel; the tile's depth-ordered list is staged through shared memory 256
-// entries at a time.  Each warp owns an 8x4-pixel sub-tile: 32 list entries are tested against the sub-tile in parallel
-// (one per lane, cull_radius2) and only the survivors are walked by the per-pixel loop, in list order.
+// Bitonic sort of n2 (power of two) 64-bit keys in shared memory by the whole CTA.
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t *keys, int n2)
+{
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+                // t-th compare-exchange of this step: partner indices i < l differ in bit j
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const uint64_t a = keys[i], c = keys[l];
+                const bool up = (i & k) == 0;
+                if ((a > c) == up) { keys[i] = c; keys[l] = a; }
+            }
+            __syncthreads();
+        }
+}
+
+// K4: one CTA per (frame, tile) sorts the tile's bucket by (depth bits, Gaussian index) — upstream's order — and emits, in list
+// order, the Gaussian index and the packed record the compositing kernels stream.  Buckets longer than kSortMax are sorted
+// kSortMax keys at a time (written back in place) and merged by rank: keys are unique, so an element's final position is
+// the number of smaller keys, i.e. the sum of its lower bounds in the sorted runs.
+__global__ void __launch_bounds__(kSortThreads)
+tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const uint32_t *__restrict__ order,
+                 const uint2 *__restrict__ ranges, const uint32_t *__restrict__ seg_start,
+                 uint64_t *__restrict__ bucket, const float2 *__restrict__ xy, const float4 *__restrict__ conic_o,
+                 const float *__restrict__ colors, uint32_t *__restrict__ point_list, float4 *__restrict__ recA,
+                 float4 *__restrict__ recB, float4 *__restrict__ recC, uint32_t *__restrict__ seg_tile,
+                 uint32_t *__restrict__ tile_maxc)
+{
+    extern __shared__ uint64_t s_keys[];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BT; i += gridDim.x * blockDim.x) tile_maxc[i] = 0u;
+    const int nactive = status[3];
+    for (int it = blockIdx.x; it < nactive; it += gridDim.x) {
+        const int blk = (int)order[it];
+        const uint2 r = ranges[blk];
+        const int n = (int)(r.y - r.x);
+        const size_t gbase = (size_t)(blk / T) * P;      // this frame's Gaussians
+        const uint32_t s0 = seg_start[blk];
+        for (int i = threadIdx.x; i < (n + kSeg - 1) / kSeg; i += blockDim.x) seg_tile[s0 + i] = (uint32_t)blk;
+
+        auto emit = [&](int rank, uint64_t key) {
+            const uint32_t idx = (uint32_t)key;
+            const size_t g = gbase + idx, o = (size_t)r.x + rank;
+            const float2 c = xy[g];
+            const float4 co = conic_o[g];
+            point_list[o] = idx;
+            recA[o] = make_float4(c.x, c.y, cull_radius2(co), __uint_as_float(idx));
+            recB[o] = co;
+            recC[o] = make_float4(colors[3 * g], colors[3 * g + 1], colors[3 * g + 2], 0.f);
+        };
+
+        if (n <= kSortMax) {
+            int n2 = 32;
+            while (n2 < n) n2 <<= 1;
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = i < n ? bucket[r.x + i] : ~0ull;
+            __syncthreads();
+            bitonic_sort_smem(s_keys, n2);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) emit(i, s_keys[i]);
+            __syncthreads();                 // s_keys is reloaded by the next tile
+            continue;
+        }
+        for (int c0 = 0; c0 < n; c0 += kSortMax) {
+            const int m = min(kSortMax, n - c0);
+            int n2 = 32;
+            while (n2 < m) n2 <<= 1;
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = i < m ? bucket[r.x + c0 + i] : ~0ull;
+            __syncthreads();
+            bitonic_sort_smem(s_keys, n2);
+            for (int i = threadIdx.x; i < m; i += blockDim.x) bucket[r.x + c0 + i] = s_keys[i];
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint64_t key = bucket[r.x + i];
+            int rank = 0;
+            for (int c0 = 0; c0 < n; c0 += kSortMax) {
+                const uint64_t *run = bucket + r.x + c0;
+                int lo = 0, hi = min(kSortMax, n - c0);
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (run[mid] < key) lo = mid + 1; else hi = mid;
+                }
+                rank += lo;
+            }
+            emit(rank, key);
+        }
+        __syncthreads();
+    }
+}
+
+// One compositing step of pixel (pxf, pyf) against a staged record: SURVEY.md §8 a-8 K6 (power > 0 skip, alpha = min(0.99, o e^p),
+// alpha < 1/255 skip, test_T < 1e-4 -> done and not blended), written without branches so that two consecutive entries
+// overlap in the pipeline (only T carries a dependence from one to the next).
+struct PixState {
+    float T, C0, C1, C2;
+    uint32_t last;
+    bool done;
+};
+
+__device__ __forceinline__ float entry_alpha(const float4 a, const float4 co, float pxf, float pyf, bool &ok)
+{
+    const float dx = a.x - pxf, dy = a.y - pyf;
+    const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
+    const float alpha = fminf(0.99f, co.w * expf(power));
+    ok = !(power > 0.f) && !(alpha < 1.0f / 255.0f);
+    return alpha;
+}
+
+__device__ __forceinline__ void blend(PixState &p, float alpha, bool ok, const float4 rgb, uint32_t pos1)
+{
+    const float test_T = p.T * (1.f - alpha);
+    const bool live = ok && !p.done;
+    const bool stop = live && test_T < 0.0001f;
+    const bool take = live && !stop;
+    const float w = take ? alpha * p.T : 0.f;
+    p.C0 += rgb.x * w; p.C1 += rgb.y * w; p.C2 += rgb.z * w;
+    p.T = take ? test_T : p.T;
+    p.last = take ? pos1 : p.last;
+    p.done = p.done || stop;
+}
+
+// K6: one CTA per (frame, 16x16 tile), one warp per 8x4-pixel sub-tile, one lane per pixel.  The warps of a CTA do not
+// synchronise with each other: each walks the tile's record stream 32 entries at a time (next chunk prefetched into
+// registers), tests the 32 against its sub-tile in parallel (one per lane, cull_radius2 precomputed by the sort kernel),
+// stages them in its own slice of shared memory and composites the ballot's survivors in list order, two at a time.
+// At every 256th list position it stores each pixel's (T, C) — the state the backward's segment CTAs start from.
 __global__ void __launch_bounds__(kBlock)
-render_fwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
-                  const float2 *__restrict__ xy, const float4 *__restrict__ conic_o, const float *__restrict__ colors,
-                  const float *__restrict__ bg, float *__restrict__ final_T, uint32_t *__restrict__ n_contrib,
+render_fwd_kernel(int H, int W, int gx, int T_tiles, const uint32_t *__restrict__ order, const uint2 *__restrict__ ranges,
+                  const uint32_t *__restrict__ seg_start,
+                  const float4 *__restrict__ recA, const float4 *__restrict__ recB, const float4 *__restrict__ recC,
+                  const float *__restrict__ bg, float4 *__restrict__ ckpt, float *__restrict__ final_T,
+                  uint32_t *__restrict__ n_contrib, float4 *__restrict__ final_state, uint32_t *__restrict__ tile_maxc,
                   float *__restrict__ out)
 {
-    // two staging buffers: the next 256 entries are fetched into registers while the current ones are composited and stored
-    // before the round's single barrier, so the gather latency hides behind the compositing
-    __shared__ float2 s_xy[2][kBlock];
-    __shared__ float4 s_co[2][kBlock];
-    __shared__ float s_rgb[2][3][kBlock];
-    __shared__ float s_rc2[2][kBlock];
+    __shared__ float4 s_a[kBlock / 32][32], s_b[kBlock / 32][32], s_c[kBlock / 32][32];
 
-    const int tid = threadIdx.y * kTile + threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int sx = blockIdx.x * kTile + (warp & 1) * 8, sy = blockIdx.y * kTile + (warp >> 1) * 4;
+    const int blk = (int)order[blockIdx.x];           // longest tile lists first
+    const int b = blk / T_tiles, tile = blk - b * T_tiles;
+    const int tx = tile % gx, ty = tile / gx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sx = tx * kTile + (warp & 1) * 8, sy = ty * kTile + (warp >> 1) * 4;
     const int px = sx + (lane & 7), py = sy + (lane >> 3);
     const float x0f = (float)sx, x1f = (float)(sx + 7), y0f = (float)sy, y1f = (float)(sy + 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
-    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-    int todo = (int)(range.y - range.x);
-    const int rounds = (todo + kBlock - 1) / kBlock;
+    const uint2 range = ranges[blk];
+    const int n = (int)(range.y - range.x);
+    const int nchunks = (n + 31) >> 5;
+    float4 *ck = ckpt + (size_t)seg_start[blk] * kBlock + tid;
 
-    bool done = !inside;
-    float T = 1.f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    uint32_t last = 0;
+    PixState p{1.f, 0.f, 0.f, 0.f, 0u, !inside};
+    float4 fa = make_float4(0.f, 0.f, -1.f, 0.f), fb = fa, fc = fa;
+    if (lane < n) { fa = recA[range.x + lane]; fb = recB[range.x + lane]; fc = recC[range.x + lane]; }
 
-    // entry of this thread in the batch being fetched
-    float2 f_xy = make_float2(0.f, 0.f); float4 f_co = make_float4(0.f, 0.f, 0.f, 0.f); float f_r = 0.f, f_g = 0.f, f_b = 0.f;
-    auto fetch = [&](int r) {
-        const uint32_t i = range.x + (uint32_t)r * kBlock + tid;
-        if (i < range.y) {
-            const uint32_t g = point_list[i];
-            f_xy = xy[g]; f_co = conic_o[g];
-            f_r = colors[3 * (size_t)g]; f_g = colors[3 * (size_t)g + 1]; f_b = colors[3 * (size_t)g + 2];
-        }
-    };
-    auto stage = [&](int b) {
-        s_xy[b][tid] = f_xy; s_co[b][tid] = f_co;
-        s_rgb[b][0][tid] = f_r; s_rgb[b][1][tid] = f_g; s_rgb[b][2][tid] = f_b;
-        s_rc2[b][tid] = cull_radius2(f_co);
-    };
-    if (rounds > 0) { fetch(0); stage(0); }
-    __syncthreads();
-
-    for (int r = 0; r < rounds; ++r, todo -= kBlock) {
-        const int b = r & 1;
-        const bool more = r + 1 < rounds;
-        if (more) fetch(r + 1);
-        const int n = min(kBlock, todo);
-        if (!__all_sync(0xffffffffu, done)) {
-            for (int j0 = 0; j0 < n; j0 += 32) {
-                const int jt = j0 + lane;
-                bool hit = false;
-                if (jt < n) hit = !(rect_dist2(s_xy[b][jt], x0f, x1f, y0f, y1f) > s_rc2[b][jt]);
-                uint32_t mask = __ballot_sync(0xffffffffu, hit);
-                while (mask) {
-                    const int j = j0 + __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    if (done) continue;
-                    const float2 c = s_xy[b][j];
-                    const float dx = c.x - pxf, dy = c.y - pyf;
-                    const float4 co = s_co[b][j];
-                    const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
-                    if (power > 0.f) continue;
-                    const float alpha = fminf(0.99f, co.w * expf(power));
-                    if (alpha < 1.0f / 255.0f) continue;
-                    const float test_T = T * (1.f - alpha);
-                    if (test_T < 0.0001f) { done = true; continue; }
-                    const float w = alpha * T;
-                    C0 += s_rgb[b][0][j] * w; C1 += s_rgb[b][1][j] * w; C2 += s_rgb[b][2][j] * w;
-                    T = test_T;
-                    last = (uint32_t)(r * kBlock + j + 1);
-                }
-                if (__all_sync(0xffffffffu, done)) break;
+    bool all_done = __all_sync(0xffffffffu, p.done);          // a sub-tile entirely outside the image
+    for (int c = 0; c < nchunks && !all_done; ++c) {
+        if ((c & 7) == 0) ck[(size_t)(c >> 3) * kBlock] = make_float4(p.T, p.C0, p.C1, p.C2);
+        const float4 a = fa, bq = fb, cq = fc;
+        const int kn = (c + 1) * 32 + lane;          // prefetch the next chunk behind this one's compositing
+        if (kn < n) { fa = recA[range.x + kn]; fb = recB[range.x + kn]; fc = recC[range.x + kn]; }
+        const bool hit = (c * 32 + lane < n) && !(rect_dist2(make_float2(a.x, a.y), x0f, x1f, y0f, y1f) > a.z);
+        uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+            __syncwarp();
+            s_a[warp][lane] = a; s_b[warp][lane] = bq; s_c[warp][lane] = cq;
+            __syncwarp();
+            const uint32_t base1 = (uint32_t)(c * 32) + 1u;
+            while (mask) {
+                const int j0 = __ffs(mask) - 1;
+                mask &= mask - 1;
+                const bool two = mask != 0;
+                const int j1 = two ? __ffs(mask) - 1 : j0;
+                mask &= mask - 1;                                   // no-op on 0
+                bool ok0, ok1;
+                const float al0 = entry_alpha(s_a[warp][j0], s_b[warp][j0], pxf, pyf, ok0);
+                const float al1 = entry_alpha(s_a[warp][j1], s_b[warp][j1], pxf, pyf, ok1);
+                blend(p, al0, ok0, s_c[warp][j0], base1 + j0);
+                blend(p, al1, ok1 && two, s_c[warp][j1], base1 + j1);
             }
+            all_done = __all_sync(0xffffffffu, p.done);
         }
-        if (more) stage(b ^ 1);          // buffer b^1 was last read in round r-1: every warp has passed that round's barrier
-        if (__syncthreads_count(done) == kBlock) break;
     }
+    const size_t HW = (size_t)H * W;
     if (inside) {
-        const size_t pid = (size_t)py * W + px, HW = (size_t)H * W;
-        final_T[pid] = T;
-        n_contrib[pid] = last;
-        out[pid] = C0 + T * bg[0];
-        out[HW + pid] = C1 + T * bg[1];
-        out[2 * HW + pid] = C2 + T * bg[2];
+        const size_t pid = (size_t)b * HW + (size_t)py * W + px;
+        final_T[pid] = p.T;
+        n_contrib[pid] = p.last;
+        float *o = out + (size_t)b * 3 * HW + (size_t)py * W + px;
+        o[0] = p.C0 + p.T * bg[0];
+        o[HW] = p.C1 + p.T * bg[1];
+        o[2 * HW] = p.C2 + p.T * bg[2];
     }
+    final_state[(size_t)blk * kBlock + tid] = make_float4(p.T, p.C0, p.C1, p.C2);
+    uint32_t m = p.last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m) atomicMax(&tile_maxc[blk], m);
 }
 
 __device__ __forceinline__ float warp_sum(float v)
@@ -440,104 +629,90 @@ __device__ __forceinline__ float warp_reduce8(float (&v)[8], int lane)
     return v[0];
 }
 
-// K7: per pixel, back to front.  Per-Gaussian gradients are reduced warp-wide with shuffles (9 per Gaussian for the 8
-// components GaussianAvatar consumes), then across the CTA's eight warps in shared memory, so each (tile, Gaussian) pair
-// issues at most one global atomic per component.  kOpacity adds dL/dopacity (API completeness; the avatar's opacity is
-// a constant without gradient, model/avatar_model.py:80).
-#ifndef GA_RENDER_BWD_MINB
-#define GA_RENDER_BWD_MINB 1
-#endif
+// K7: one CTA per 256-entry SEGMENT of a tile list; all segments of all tiles of all frames run in parallel.  Inside a
+// segment the replay is upstream's: back to front, T <- T / (1 - alpha), the colour behind the entry by the recurrence
+// acc <- last_alpha * last_colour + (1 - last_alpha) * acc.  A pixel whose blended entries continue past the segment starts
+// from the forward's checkpoint behind it: T = T_ckpt and acc = (C_final - C_ckpt) / T_ckpt (the colour composited behind the
+// checkpoint, un-premultiplied); a pixel whose last contributor lies inside the segment starts from (T_final, 0) as upstream
+// does.  Per-Gaussian gradients are reduced warp-wide with shuffles (9 for the 8 components GaussianAvatar consumes), across
+// the CTA's eight warps in shared memory, then leave as one vector reduction per (segment entry, array).
 template <bool kOpacity>
-__global__ void __launch_bounds__(kBlock, GA_RENDER_BWD_MINB)
-render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t *__restrict__ point_list,
-                  const float *__restrict__ bg, const float2 *__restrict__ xy, const float4 *__restrict__ conic_o,
-                  const float *__restrict__ colors, const float *__restrict__ final_T,
+__global__ void __launch_bounds__(kBlock)
+render_bwd_kernel(int H, int W, int gx, int T_tiles, int P, const int32_t *__restrict__ status,
+                  const uint32_t *__restrict__ seg_tile, const uint32_t *__restrict__ seg_start,
+                  const uint2 *__restrict__ ranges, const uint32_t *__restrict__ tile_maxc,
+                  const float4 *__restrict__ recA, const float4 *__restrict__ recB, const float4 *__restrict__ recC,
+                  const float4 *__restrict__ ckpt, const float *__restrict__ bg, const float4 *__restrict__ final_state,
                   const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dout,
                   float2 *__restrict__ d_mean2D, float4 *__restrict__ d_conic_op, float *__restrict__ d_colors)
 {
-    // staging and accumulators are double-buffered: round r composites buffer r & 1 while the entries of round r + 1 sit in
-    // registers (stored before the round's single barrier) and the previous round's accumulators are flushed after it
-    __shared__ uint32_t s_id[2][kBlock];
-    __shared__ float2 s_xy[2][kBlock];
-    __shared__ float4 s_co[2][kBlock];
-    __shared__ float s_rgb[2][3][kBlock];
-    __shared__ float s_acc[2][9][kBlock];
-    __shared__ float s_rc2[2][kBlock];
-    __shared__ uint32_t s_max[kBlock / 32];
+    __shared__ float4 s_a[kSeg], s_b[kSeg], s_c[kSeg];
+    __shared__ float s_acc[9][kSeg];
 
-    const int tid = threadIdx.y * kTile + threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int sx = blockIdx.x * kTile + (warp & 1) * 8, sy = blockIdx.y * kTile + (warp >> 1) * 4;      // 8x4 sub-tile per warp
+    const int g = blockIdx.x;
+    if (g >= status[2]) return;
+    const int blk = (int)seg_tile[g];
+    const int seg = g - (int)seg_start[blk];
+    const uint32_t maxc = tile_maxc[blk];
+    const uint32_t lo = (uint32_t)seg * kSeg;                 // first list position of this segment
+    if (lo >= maxc) return;                                   // nothing blended at or behind this segment: uniform for the CTA
+    const uint2 range = ranges[blk];
+    const uint32_t hi = min(min(range.y - range.x, lo + kSeg), maxc);   // positions [lo, hi) are replayed, back to front
+    const int cnt = (int)(hi - lo);
+
+    const int b = blk / T_tiles, tile = blk - b * T_tiles;
+    const int tx = tile % gx, ty = tile / gx;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sx = tx * kTile + (warp & 1) * 8, sy = ty * kTile + (warp >> 1) * 4;
     const int px = sx + (lane & 7), py = sy + (lane >> 3);
     const float x0f = (float)sx, x1f = (float)(sx + 7), y0f = (float)sy, y1f = (float)(sy + 3);
     const bool inside = px < W && py < H;
     const float pxf = (float)px, pyf = (float)py;
-    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-    if (range.y <= range.x) return;  // uniform for the CTA
+    const size_t HW = (size_t)H * W, pid = (size_t)py * W + px;
 
-    const size_t pid = (size_t)py * W + px, HW = (size_t)H * W;
-    const float T_final = inside ? final_T[pid] : 0.f;
-    const uint32_t last_contributor = inside ? n_contrib[pid] : 0u;
+    // stage the segment back to front: slot j holds list position hi - 1 - j
+    if (tid < cnt) {
+        const size_t o = (size_t)range.x + (hi - 1 - tid);
+        s_a[tid] = recA[o]; s_b[tid] = recB[o]; s_c[tid] = recC[o];
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) s_acc[k][tid] = 0.f;
+
+    const float4 fs = final_state[(size_t)blk * kBlock + tid];
+    const float T_final = inside ? fs.x : 0.f;
+    const uint32_t last_contributor = inside ? n_contrib[(size_t)b * HW + pid] : 0u;
     float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f;
-    if (inside) { dpix0 = dL_dout[pid]; dpix1 = dL_dout[HW + pid]; dpix2 = dL_dout[2 * HW + pid]; }
+    if (inside) {
+        const float *d = dL_dout + (size_t)b * 3 * HW + pid;
+        dpix0 = d[0]; dpix1 = d[HW]; dpix2 = d[2 * HW];
+    }
     const float bg_dot = bg[0] * dpix0 + bg[1] * dpix1 + bg[2] * dpix2;
-
-    // nothing past the furthest blended entry of any pixel of this tile contributes
-    uint32_t m = last_contributor;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) s_max[warp] = m;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { s_acc[0][k][tid] = 0.f; s_acc[1][k][tid] = 0.f; }
-    __syncthreads();
-    uint32_t todo = 0;
-#pragma unroll
-    for (int w = 0; w < kBlock / 32; ++w) todo = max(todo, s_max[w]);
-    if (todo == 0) return;
-
-    float T = T_final;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
+    float T = T_final, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+    if (last_contributor > lo + kSeg) {            // blended entries continue behind this segment
+        const float4 ck = ckpt[((size_t)seg_start[blk] + seg + 1) * kBlock + tid];
+        const float inv = 1.f / ck.x;
+        T = ck.x;
+        acc0 = (fs.y - ck.y) * inv; acc1 = (fs.z - ck.z) * inv; acc2 = (fs.w - ck.w) * inv;
+    }
+    float lc0 = 0.f, lc1 = 0.f, lc2 = 0.f, last_alpha = 0.f;
     const float ddelx_dx = 0.5f * (float)W, ddely_dy = 0.5f * (float)H;
-    const int rounds = (int)((todo + kBlock - 1) / kBlock);
     const int vidx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // component this lane ends up owning
-
-    uint32_t f_id = 0; float2 f_xy = make_float2(0.f, 0.f); float4 f_co = make_float4(0.f, 0.f, 0.f, 0.f); float f_r = 0.f, f_g = 0.f, f_b = 0.f;
-    auto fetch = [&](int r) {
-        const uint32_t progress = (uint32_t)r * kBlock + tid;
-        if (progress < todo) {
-            f_id = point_list[range.x + todo - 1 - progress];
-            f_xy = xy[f_id]; f_co = conic_o[f_id];
-            f_r = colors[3 * (size_t)f_id]; f_g = colors[3 * (size_t)f_id + 1]; f_b = colors[3 * (size_t)f_id + 2];
-        }
-    };
-    auto stage = [&](int b) {
-        s_id[b][tid] = f_id; s_xy[b][tid] = f_xy; s_co[b][tid] = f_co;
-        s_rgb[b][0][tid] = f_r; s_rgb[b][1][tid] = f_g; s_rgb[b][2][tid] = f_b;
-        s_rc2[b][tid] = cull_radius2(f_co);
-    };
-    fetch(0); stage(0);
     __syncthreads();
 
-    for (int r = 0; r < rounds; ++r) {
-        const int b = r & 1;
-        const bool more = r + 1 < rounds;
-        const bool have = (uint32_t)r * kBlock + tid < todo;
-        if (more) fetch(r + 1);
-        const int n = (int)min((uint32_t)kBlock, todo - (uint32_t)r * kBlock);
-        for (int j0 = 0; j0 < n; j0 += 32) {
-          const int jt = j0 + lane;
-          bool hit = false;
-          if (jt < n) hit = !(rect_dist2(s_xy[b][jt], x0f, x1f, y0f, y1f) > s_rc2[b][jt]);
-          uint32_t mask = __ballot_sync(0xffffffffu, hit);
-          while (mask) {
+    for (int j0 = 0; j0 < cnt; j0 += 32) {
+        const int jt = j0 + lane;
+        bool hit = false;
+        if (jt < cnt) { const float4 a = s_a[jt]; hit = !(rect_dist2(make_float2(a.x, a.y), x0f, x1f, y0f, y1f) > a.z); }
+        uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
             const int j = j0 + __ffs(mask) - 1;
             mask &= mask - 1;
-            const uint32_t index = todo - 1 - ((uint32_t)r * kBlock + j);  // 0-based position in the tile list
+            const uint32_t index = hi - 1 - (uint32_t)j;            // 0-based position in the tile list
             bool active = index < last_contributor;
-            float2 c; float4 co; float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
+            float4 co; float dx = 0.f, dy = 0.f, G = 0.f, alpha = 0.f;
             if (active) {
-                c = s_xy[b][j]; co = s_co[b][j];
-                dx = c.x - pxf; dy = c.y - pyf;
+                const float4 a = s_a[j]; co = s_b[j];
+                dx = a.x - pxf; dy = a.y - pyf;
                 const float power = -0.5f * (co.x * dx * dx + co.z * dy * dy) - co.y * dx * dy;
                 if (power > 0.f) active = false;
                 else {
@@ -554,11 +729,11 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
             if (active) {
                 T = T / (1.f - alpha);
                 const float dchannel_dcolor = alpha * T;
-                const float col0 = s_rgb[b][0][j], col1 = s_rgb[b][1][j], col2 = s_rgb[b][2][j];
-                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = col0;
-                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = col1;
-                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = col2;
-                float dL_dalpha = (col0 - acc0) * dpix0 + (col1 - acc1) * dpix1 + (col2 - acc2) * dpix2;
+                const float4 col = s_c[j];
+                acc0 = last_alpha * lc0 + (1.f - last_alpha) * acc0; lc0 = col.x;
+                acc1 = last_alpha * lc1 + (1.f - last_alpha) * acc1; lc1 = col.y;
+                acc2 = last_alpha * lc2 + (1.f - last_alpha) * acc2; lc2 = col.z;
+                float dL_dalpha = (col.x - acc0) * dpix0 + (col.y - acc1) * dpix1 + (col.z - acc2) * dpix2;
                 v[0] = dchannel_dcolor * dpix0; v[1] = dchannel_dcolor * dpix1; v[2] = dchannel_dcolor * dpix2;
                 dL_dalpha *= T;
                 last_alpha = alpha;
@@ -575,48 +750,50 @@ render_bwd_kernel(int H, int W, const uint2 *__restrict__ ranges, const uint32_t
                 vo = G * dL_dalpha;
             }
             const float red = warp_reduce8(v, lane);
-            if ((lane & 3) == 0) atomicAdd(&s_acc[b][vidx][j], red);
+            if ((lane & 3) == 0) atomicAdd(&s_acc[vidx][j], red);
             if (kOpacity) {
                 vo = warp_sum(vo);
-                if (lane == 0) atomicAdd(&s_acc[b][8][j], vo);
+                if (lane == 0) atomicAdd(&s_acc[8][j], vo);
             }
-          }
         }
-        if (more) stage(b ^ 1);      // buffer b^1 was last read in round r-1, whose barrier every warp has passed
-        __syncthreads();
-        if (have) {
-            const uint32_t g = s_id[b][tid];
-            float a[9];
+    }
+    __syncthreads();
+    if (tid < cnt) {
+        const size_t gi = (size_t)b * P + __float_as_uint(s_a[tid].w);
+        float a[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) { a[k] = s_acc[b][k][tid]; s_acc[b][k][tid] = 0.f; }      // reused in round r+2, after the next barrier
-            if (a[0] != 0.f) atomicAdd(&d_colors[3 * (size_t)g], a[0]);
-            if (a[1] != 0.f) atomicAdd(&d_colors[3 * (size_t)g + 1], a[1]);
-            if (a[2] != 0.f) atomicAdd(&d_colors[3 * (size_t)g + 2], a[2]);
-            // 8- and 16-byte vector reductions (sm_90+): one L2 atomic per float2 / float4 instead of one per component
-            if (a[3] != 0.f || a[4] != 0.f)
-                asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(&d_mean2D[g]), "f"(a[3]), "f"(a[4]) : "memory");
-            if (a[5] != 0.f || a[6] != 0.f || a[7] != 0.f || (kOpacity && a[8] != 0.f))
-                red_add_v4(&d_conic_op[g].x, a[5], a[6], a[7], kOpacity ? a[8] : 0.f);
-        }
+        for (int k = 0; k < 9; ++k) a[k] = s_acc[k][tid];
+        if (a[0] != 0.f) atomicAdd(&d_colors[3 * gi], a[0]);
+        if (a[1] != 0.f) atomicAdd(&d_colors[3 * gi + 1], a[1]);
+        if (a[2] != 0.f) atomicAdd(&d_colors[3 * gi + 2], a[2]);
+        // 8- and 16-byte vector reductions (sm_90+): one L2 atomic per float2 / float4 instead of one per component
+        if (a[3] != 0.f || a[4] != 0.f)
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(&d_mean2D[gi]), "f"(a[3]), "f"(a[4]) : "memory");
+        if (a[5] != 0.f || a[6] != 0.f || a[7] != 0.f || (kOpacity && a[8] != 0.f))
+            red_add_v4(&d_conic_op[gi].x, a[5], a[6], a[7], kOpacity ? a[8] : 0.f);
     }
 }
 
 // Fused K8 (conic -> cov2D -> cov3D / mean) + K9 (mean2D -> mean3D, cov3D -> scale / rotation): one thread per Gaussian.
 __global__ void __launch_bounds__(256)
-preprocess_bwd_kernel(int P, int H, int W, float tanfovx, float tanfovy, float mod, const float *__restrict__ means3D,
-                      const float *__restrict__ scales, const float *__restrict__ rots,
-                      const float *__restrict__ view_g, const float *__restrict__ proj_g,
+preprocess_bwd_kernel(int P, int H, int W, CamSrc cam, float mod, const float *__restrict__ means3D,
+                      const float *__restrict__ scales, const float *__restrict__ rots, long long rot_stride,
                       const int32_t *__restrict__ radii, const float *__restrict__ cov3d,
                       const float2 *__restrict__ d_mean2D, const float4 *__restrict__ d_conic_op,
                       float *__restrict__ d_means3D, float *__restrict__ d_scales, float *__restrict__ d_rots,
                       float *__restrict__ d_opac, float *__restrict__ d_means2D_out)
 {
+    const int fb = blockIdx.y;
     __shared__ float view[16], proj[16];
-    if (threadIdx.x < 16) view[threadIdx.x] = view_g[threadIdx.x];
-    else if (threadIdx.x < 32) proj[threadIdx.x - 16] = proj_g[threadIdx.x - 16];
+    if (threadIdx.x < 16) view[threadIdx.x] = cam.view[(size_t)fb * cam.stride + threadIdx.x];
+    else if (threadIdx.x < 32) proj[threadIdx.x - 16] = cam.proj[(size_t)fb * cam.stride + threadIdx.x - 16];
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
+    const float tanfovx = cam.tan ? cam.tan[(size_t)fb * cam.stride] : cam.tanx;
+    const float tanfovy = cam.tan ? cam.tan[(size_t)fb * cam.stride + 1] : cam.tany;
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    if (il >= P) return;
+    const size_t i = (size_t)fb * P + il;
+    const float *rq = rots + (size_t)fb * rot_stride + 4 * (size_t)il;
     const size_t i3 = 3 * (size_t)i;
     const float4 gco = d_conic_op[i];
     const float2 g2 = d_mean2D[i];
@@ -695,7 +872,7 @@ preprocess_bwd_kernel(int P, int H, int W, float tanfovx, float tanfovy, float m
     d_means3D[i3] = dmean[0]; d_means3D[i3 + 1] = dmean[1]; d_means3D[i3 + 2] = dmean[2];
 
     const float sv[3] = {mod * scales[i3], mod * scales[i3 + 1], mod * scales[i3 + 2]};
-    const float qr = rots[4 * (size_t)i], qx = rots[4 * (size_t)i + 1], qy = rots[4 * (size_t)i + 2], qz = rots[4 * (size_t)i + 3];
+    const float qr = rq[0], qx = rq[1], qy = rq[2], qz = rq[3];
     float Rm[3][3];
     quat_to_rot(qr, qx, qy, qz, Rm);
     const float dS[3][3] = {{dc[0], 0.5f * dc[1], 0.5f * dc[2]}, {0.5f * dc[1], dc[3], 0.5f * dc[4]}, {0.5f * dc[2], 0.5f * dc[4], dc[5]}};
@@ -729,177 +906,302 @@ preprocess_bwd_kernel(int P, int H, int W, float tanfovx, float tanfovy, float m
     }
 }
 
+int check_dims(int B, int P, int H, int W)
+{
+    GA_REQUIRE(B >= 1 && B <= 8, "bad frame count B=%d (1..8)", B);
+    GA_REQUIRE(P >= 0 && H > 0 && W > 0, "bad raster dims P=%d H=%d W=%d", P, H, W);
+    GA_REQUIRE(cdiv(W, kTile) <= 65535 && cdiv(H, kTile) <= 65535, "image too large");
+    GA_REQUIRE((long long)B * cdiv(W, kTile) * cdiv(H, kTile) < (1ll << 30), "too many tiles");
+    return GA_OK;
+}
 int check_settings(const GaRasterSettings *s)
 {
     GA_REQUIRE(s != nullptr, "settings is NULL");
-    GA_REQUIRE(s->P >= 0 && s->H > 0 && s->W > 0, "bad raster dims P=%d H=%d W=%d", s->P, s->H, s->W);
-    GA_REQUIRE(cdiv(s->W, kTile) <= 65535 && cdiv(s->H, kTile) <= 65535, "image too large");
+    return check_dims(1, s->P, s->H, s->W);
+}
+
+struct FwdArgs {
+    const float *means3D, *colors, *scales, *rotations, *opacities, *bg;
+    long long rot_stride, opac_stride;
+    float mod;
+};
+
+// K1 + K2 for all frames.
+int launch_preprocess(const Dims &d, const CamSrc &cam, const FwdArgs &a, long long capacity, const GeomViews &g, const ImgViews &iv,
+                      int32_t *radii, cudaStream_t stream)
+{
+    const size_t BT = (size_t)d.B * d.T;
+    GA_CHECK_CUDA(cudaMemsetAsync(iv.count, 0, sizeof(uint32_t) * BT, stream));
+    if (d.P > 0) {
+        ProfScope _ps("preprocess_fwd_kernel", stream);
+        preprocess_fwd_kernel<<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.H, d.W, d.gx, d.gy, cam, a.mod, a.means3D, a.scales,
+                                                                            a.rotations, a.rot_stride, a.opacities, a.opac_stride, g.depth,
+                                                                            g.xy, g.conic_o, g.cov3d, g.tiles, g.rect, radii, iv.count);
+        GA_CHECK_LAUNCH("preprocess_fwd_kernel");
+    }
+    {
+        ProfScope _ps("tile_scan_kernel", stream);
+        tile_scan_kernel<<<1, 1024, 0, stream>>>((int)BT, d.T, capacity, iv.count, iv.ranges, iv.cursor, iv.seg_start, iv.order, iv.status);
+    }
+    GA_CHECK_LAUNCH("tile_scan_kernel");
     return GA_OK;
 }
+
+// K3 + K4 + K6 for all frames.
+int launch_binning_and_render(const Dims &d, const FwdArgs &a, long long capacity, const GeomViews &g, const ImgViews &iv, const BinViews &bv,
+                              float *out_color, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        GA_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMax * (int)sizeof(uint64_t)));
+        attr_set = true;
+    }
+    const int BT = d.B * d.T;
+    if (d.P > 0) {
+        {
+            ProfScope _ps("bucket_scatter_kernel", stream);
+            bucket_scatter_kernel<<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.gx, d.T, capacity, g.depth, g.tiles, g.rect, iv.cursor,
+                                                                                bv.bucket);
+        }
+        GA_CHECK_LAUNCH("bucket_scatter_kernel");
+    }
+    {
+        ProfScope _ps("tile_sort_kernel", stream);
+        tile_sort_kernel<<<min(BT, 3 * num_sms()), kSortThreads, kSortMax * sizeof(uint64_t), stream>>>(
+            d.P, d.T, BT, iv.status, iv.order, iv.ranges, iv.seg_start, bv.bucket, g.xy, g.conic_o, a.colors, bv.point_list, bv.recA, bv.recB,
+            bv.recC, bv.seg_tile, iv.tile_maxc);
+    }
+    GA_CHECK_LAUNCH("tile_sort_kernel");
+    {
+        ProfScope _ps("render_fwd_kernel", stream);
+        render_fwd_kernel<<<BT, kBlock, 0, stream>>>(d.H, d.W, d.gx, d.T, iv.order, iv.ranges, iv.seg_start, bv.recA, bv.recB, bv.recC, a.bg, bv.ckpt,
+                                                    iv.final_T, iv.n_contrib, iv.final_state, iv.tile_maxc, out_color);
+    }
+    GA_CHECK_LAUNCH("render_fwd_kernel");
+    return GA_OK;
+}
+
+struct BwdArgs {
+    const float *means3D, *colors, *scales, *rotations, *bg, *dL_dout;
+    long long rot_stride;
+    float mod;
+    float *d_means3D, *d_colors, *d_scales, *d_rotations, *d_opacities, *d_means2D;
+};
+
+size_t bwd_scratch_bytes(size_t BP)
+{
+    const size_t n = BP > 0 ? BP : 1;
+    return align_up(n * sizeof(float2)) + align_up(n * sizeof(float4));
+}
+
+int launch_backward(const Dims &d, const CamSrc &cam, const BwdArgs &a, const int32_t *radii, const GeomViews &g, const ImgViews &iv,
+                    const BinViews &bv, void *scratch, cudaStream_t stream)
+{
+    const size_t BP = (size_t)d.B * d.P;
+    Carver sc(scratch);
+    float2 *d_mean2D = sc.take<float2>(BP);
+    float4 *d_conic_op = sc.take<float4>(BP);
+    GA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, bwd_scratch_bytes(BP), stream));
+    GA_CHECK_CUDA(cudaMemsetAsync(a.d_colors, 0, sizeof(float) * 3 * BP, stream));
+    {
+        ProfScope _ps("render_bwd_kernel", stream);
+        const int grid = (int)bv.max_segments;
+        if (a.d_opacities)
+            render_bwd_kernel<true><<<grid, kBlock, 0, stream>>>(d.H, d.W, d.gx, d.T, d.P, iv.status, bv.seg_tile, iv.seg_start, iv.ranges,
+                                                                 iv.tile_maxc, bv.recA, bv.recB, bv.recC, bv.ckpt, a.bg, iv.final_state,
+                                                                 iv.n_contrib, a.dL_dout, d_mean2D, d_conic_op, a.d_colors);
+        else
+            render_bwd_kernel<false><<<grid, kBlock, 0, stream>>>(d.H, d.W, d.gx, d.T, d.P, iv.status, bv.seg_tile, iv.seg_start, iv.ranges,
+                                                                  iv.tile_maxc, bv.recA, bv.recB, bv.recC, bv.ckpt, a.bg, iv.final_state,
+                                                                  iv.n_contrib, a.dL_dout, d_mean2D, d_conic_op, a.d_colors);
+    }
+    GA_CHECK_LAUNCH("render_bwd_kernel");
+    {
+        ProfScope _ps("preprocess_bwd_kernel", stream);
+        preprocess_bwd_kernel<<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.H, d.W, cam, a.mod, a.means3D, a.scales, a.rotations,
+                                                                            a.rot_stride, radii, g.cov3d, d_mean2D, d_conic_op, a.d_means3D,
+                                                                            a.d_scales, a.d_rotations, a.d_opacities, a.d_means2D);
+    }
+    GA_CHECK_LAUNCH("preprocess_bwd_kernel");
+    return GA_OK;
+}
+
+constexpr long long kNoCapacity = 0x7fffffffll;   // per-frame API: the host sizes the binning buffer after reading the count
 
 }  // namespace
 }  // namespace ga
 
 using namespace ga;
 
-extern "C" size_t ga_raster_geom_bytes(int32_t P) { return carve_geom(nullptr, P).total; }
-extern "C" size_t ga_raster_img_bytes(int32_t H, int32_t W) { return carve_img(nullptr, H, W).total; }
-extern "C" size_t ga_raster_binning_bytes(int64_t R, int32_t H, int32_t W) { return carve_bin(nullptr, R, H, W).total; }
-extern "C" size_t ga_raster_bwd_scratch_bytes(int32_t P)
-{
-    const size_t n = P > 0 ? (size_t)P : 1;
-    return align_up(n * sizeof(float2)) + align_up(n * sizeof(float4));
-}
+// ---- per-frame API (upstream's call shape: the host reads the instance count to size the binning buffer) -------------------
+extern "C" size_t ga_raster_geom_bytes(int32_t P) { return carve_geom(nullptr, (size_t)(P > 0 ? P : 0)).total; }
+extern "C" size_t ga_raster_img_bytes(int32_t H, int32_t W) { return carve_img(nullptr, make_dims(1, 0, H, W)).total; }
+extern "C" size_t ga_raster_binning_bytes(int64_t R, int32_t H, int32_t W) { return carve_bin(nullptr, R, make_dims(1, 0, H, W)).total; }
+extern "C" size_t ga_raster_bwd_scratch_bytes(int32_t P) { return bwd_scratch_bytes((size_t)(P > 0 ? P : 0)); }
 
 extern "C" int ga_raster_forward_preprocess(const GaRasterSettings *s, const float *means3D, const float *scales,
                                             const float *rotations, const float *opacities, const float *viewmatrix,
-                                            const float *projmatrix, void *geom, int32_t *radii,
+                                            const float *projmatrix, void *geom, void *img, int32_t *radii,
                                             int64_t *num_rendered_host, void *stream_)
 {
     if (int rc = check_settings(s)) return rc;
-    GA_REQUIRE(num_rendered_host, "num_rendered_host is NULL");
+    GA_REQUIRE(num_rendered_host && img, "NULL pointer argument");
     *num_rendered_host = 0;
-    if (s->P == 0) return GA_OK;
-    GA_REQUIRE(means3D && scales && rotations && opacities && viewmatrix && projmatrix && geom && radii, "NULL pointer argument");
+    GA_REQUIRE(s->P == 0 || (means3D && scales && rotations && opacities && viewmatrix && projmatrix && geom && radii), "NULL pointer argument");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    GeomViews g = carve_geom(geom, s->P);
-    const int gx = cdiv(s->W, kTile), gy = cdiv(s->H, kTile);
-    {
-        ProfScope _ps("preprocess_fwd_kernel", stream);
-        preprocess_fwd_kernel<<<cdiv(s->P, 256), 256, 0, stream>>>(s->P, s->H, s->W, gx, gy, s->tanfovx, s->tanfovy,
-                                                                  s->scale_modifier, means3D, scales, rotations, opacities,
-                                                                  viewmatrix, projmatrix, g.depth, g.xy, g.conic_o, g.cov3d,
-                                                                  g.tiles, g.rect, radii);
-    }
-    GA_CHECK_LAUNCH("preprocess_fwd_kernel");
-    size_t tb = g.scan_temp_bytes;
-    {
-        ProfScope _ps("cub_inclusive_sum", stream);
-        GA_CHECK_CUDA(cub::DeviceScan::InclusiveSum(g.scan_temp, tb, g.tiles, g.offsets, s->P, stream));
-    }
-    uint32_t total = 0;
-    GA_CHECK_CUDA(cudaMemcpyAsync(&total, g.offsets + (s->P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    const Dims d = make_dims(1, s->P, s->H, s->W);
+    GeomViews g = carve_geom(geom, (size_t)s->P);
+    ImgViews iv = carve_img(img, d);
+    const CamSrc cam{viewmatrix, projmatrix, nullptr, 0, s->tanfovx, s->tanfovy};
+    const FwdArgs a{means3D, nullptr, scales, rotations, opacities, nullptr, 0, 0, s->scale_modifier};
+    if (int rc = launch_preprocess(d, cam, a, kNoCapacity, g, iv, radii, stream)) return rc;
+    int32_t total = 0;
+    GA_CHECK_CUDA(cudaMemcpyAsync(&total, iv.status, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     GA_CHECK_CUDA(cudaStreamSynchronize(stream));
     *num_rendered_host = (int64_t)total;
     return GA_OK;
 }
 
-extern "C" int ga_raster_forward_render(const GaRasterSettings *s, const float *colors, const float *bg, void *geom,
-                                        void *binning, size_t binning_bytes, int64_t R, void *img, float *out_color,
-                                        void *stream_)
+extern "C" int ga_raster_forward_render(const GaRasterSettings *s, const float *colors, const float *bg, void *geom, void *binning,
+                                        size_t binning_bytes, int64_t R, void *img, float *out_color, void *stream_)
 {
     if (int rc = check_settings(s)) return rc;
-    GA_REQUIRE(bg && img && out_color, "NULL pointer argument");
-    GA_REQUIRE(R >= 0 && R < (int64_t)0x7fffffff, "num_rendered out of range: %lld", (long long)R);
+    GA_REQUIRE(bg && img && out_color && binning, "NULL pointer argument");
+    GA_REQUIRE(R >= 0 && R < (int64_t)kNoCapacity, "num_rendered out of range: %lld", (long long)R);
+    GA_REQUIRE(s->P == 0 || (colors && geom), "NULL pointer argument");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int gx = cdiv(s->W, kTile), gy = cdiv(s->H, kTile);
-    ImgViews iv = carve_img(img, s->H, s->W);
-    GA_CHECK_CUDA(cudaMemsetAsync(iv.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
-    BinViews b{};
-    if (R > 0) {
-        GA_REQUIRE(colors && geom && binning, "NULL pointer argument");
-        b = carve_bin(binning, R, s->H, s->W);
-        if (b.total > binning_bytes) {
-            set_error("binning buffer too small: need %zu bytes, have %zu", b.total, binning_bytes);
-            return GA_ERR_CAPACITY;
-        }
-        GeomViews g = carve_geom(geom, s->P);
-        {
-            ProfScope _ps("duplicate_with_keys_kernel", stream);
-            duplicate_with_keys_kernel<<<cdiv(s->P, 256), 256, 0, stream>>>(s->P, gx, g.depth, g.offsets, g.tiles, g.rect,
-                                                                           b.keys_unsorted, b.vals_unsorted);
-        }
-        GA_CHECK_LAUNCH("duplicate_with_keys_kernel");
-        size_t tb = b.sort_temp_bytes;
-        {
-            ProfScope _ps("cub_radix_sort_pairs", stream);
-            GA_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(b.sort_temp, tb, b.keys_unsorted, b.keys, b.vals_unsorted, b.vals,
-                                                          (int)R, 0, sort_end_bit(s->H, s->W), stream));
-        }
-        {
-            ProfScope _ps("tile_ranges_kernel", stream);
-            tile_ranges_kernel<<<cdiv(R, 256), 256, 0, stream>>>(R, b.keys, iv.ranges);
-        }
-        GA_CHECK_LAUNCH("tile_ranges_kernel");
+    const Dims d = make_dims(1, s->P, s->H, s->W);
+    BinViews bv = carve_bin(binning, R, d);
+    if (bv.total > binning_bytes) {
+        set_error("binning buffer too small: need %zu bytes, have %zu", bv.total, binning_bytes);
+        return GA_ERR_CAPACITY;
     }
-    GeomViews g = carve_geom(geom, s->P);
-    {
-        ProfScope _ps("render_fwd_kernel", stream);
-        render_fwd_kernel<<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, g.xy, g.conic_o,
-                                                                          colors, bg, iv.final_T, iv.n_contrib, out_color);
-    }
-    GA_CHECK_LAUNCH("render_fwd_kernel");
-    return GA_OK;
+    const FwdArgs a{nullptr, colors, nullptr, nullptr, nullptr, bg, 0, 0, s->scale_modifier};
+    return launch_binning_and_render(d, a, R, carve_geom(geom, (size_t)s->P), carve_img(img, d), bv, out_color, stream);
 }
 
-extern "C" int ga_raster_backward(const GaRasterSettings *s, const float *means3D, const float *colors,
-                                  const float *scales, const float *rotations, const float *bg, const float *viewmatrix,
-                                  const float *projmatrix, const int32_t *radii, const void *geom, const void *binning,
-                                  const void *img, int64_t R, const float *dL_dout, void *scratch, float *d_means3D,
-                                  float *d_colors, float *d_scales, float *d_rotations, float *d_opacities,
-                                  float *d_means2D, void *stream_)
+extern "C" int ga_raster_backward(const GaRasterSettings *s, const float *means3D, const float *colors, const float *scales,
+                                  const float *rotations, const float *bg, const float *viewmatrix, const float *projmatrix,
+                                  const int32_t *radii, const void *geom, const void *binning, const void *img, int64_t R,
+                                  const float *dL_dout, void *scratch, float *d_means3D, float *d_colors, float *d_scales,
+                                  float *d_rotations, float *d_opacities, float *d_means2D, void *stream_)
 {
     if (int rc = check_settings(s)) return rc;
     if (s->P == 0) return GA_OK;
-    GA_REQUIRE(means3D && colors && scales && rotations && bg && viewmatrix && projmatrix && radii && geom && img &&
+    GA_REQUIRE(means3D && colors && scales && rotations && bg && viewmatrix && projmatrix && radii && geom && img && binning &&
                    dL_dout && scratch && d_means3D && d_colors && d_scales,
                "NULL pointer argument");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int gx = cdiv(s->W, kTile), gy = cdiv(s->H, kTile);
-    GeomViews g = carve_geom(const_cast<void *>(geom), s->P);
-    ImgViews iv = carve_img(const_cast<void *>(img), s->H, s->W);
-    Carver sc(scratch);
-    float2 *d_mean2D = sc.take<float2>(s->P);
-    float4 *d_conic_op = sc.take<float4>(s->P);
-    GA_CHECK_CUDA(cudaMemsetAsync(scratch, 0, ga_raster_bwd_scratch_bytes(s->P), stream));
-    GA_CHECK_CUDA(cudaMemsetAsync(d_colors, 0, sizeof(float) * 3 * (size_t)s->P, stream));
-    if (R > 0) {
-        GA_REQUIRE(binning, "NULL binning buffer");
-        BinViews b = carve_bin(const_cast<void *>(binning), R, s->H, s->W);
-        {
-            ProfScope _ps("render_bwd_kernel", stream);
-            if (d_opacities)
-                render_bwd_kernel<true><<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, bg, g.xy,
-                                                                              g.conic_o, colors, iv.final_T, iv.n_contrib,
-                                                                              dL_dout, d_mean2D, d_conic_op, d_colors);
-            else
-                render_bwd_kernel<false><<<dim3(gx, gy), dim3(kTile, kTile), 0, stream>>>(s->H, s->W, iv.ranges, b.vals, bg, g.xy,
-                                                                              g.conic_o, colors, iv.final_T, iv.n_contrib,
-                                                                              dL_dout, d_mean2D, d_conic_op, d_colors);
-        }
-        GA_CHECK_LAUNCH("render_bwd_kernel");
-    }
-    {
-        ProfScope _ps("preprocess_bwd_kernel", stream);
-        preprocess_bwd_kernel<<<cdiv(s->P, 256), 256, 0, stream>>>(s->P, s->H, s->W, s->tanfovx, s->tanfovy, s->scale_modifier,
-                                                                  means3D, scales, rotations, viewmatrix, projmatrix, radii,
-                                                                  g.cov3d, d_mean2D, d_conic_op, d_means3D, d_scales,
-                                                                  d_rotations, d_opacities, d_means2D);
-    }
-    GA_CHECK_LAUNCH("preprocess_bwd_kernel");
+    const Dims d = make_dims(1, s->P, s->H, s->W);
+    const CamSrc cam{viewmatrix, projmatrix, nullptr, 0, s->tanfovx, s->tanfovy};
+    const BwdArgs a{means3D, colors, scales, rotations, bg, dL_dout, 0, s->scale_modifier, d_means3D, d_colors, d_scales, d_rotations,
+                    d_opacities, d_means2D};
+    return launch_backward(d, cam, a, radii, carve_geom(const_cast<void *>(geom), (size_t)s->P), carve_img(const_cast<void *>(img), d),
+                           carve_bin(const_cast<void *>(binning), R, d), scratch, stream);
+}
+
+// ---- batched API: every frame of a step in one set of launches, no host read-back ------------------------------------------
+static int check_batch(const GaRasterBatchDesc *d)
+{
+    GA_REQUIRE(d != nullptr, "batch descriptor is NULL");
+    if (int rc = check_dims(d->B, d->P, d->H, d->W)) return rc;
+    GA_REQUIRE(d->capacity >= 0 && d->capacity < (int64_t)kNoCapacity, "capacity out of range: %lld", (long long)d->capacity);
+    GA_REQUIRE((d->rot_stride == 0 || d->rot_stride == 4ll * d->P) && (d->opac_stride == 0 || d->opac_stride == (long long)d->P),
+               "rot_stride / opac_stride must be 0 (shared) or one frame");
+    return GA_OK;
+}
+extern "C" size_t ga_rasterb_geom_bytes(int32_t B, int32_t P) { return carve_geom(nullptr, (size_t)B * (size_t)(P > 0 ? P : 0)).total; }
+extern "C" size_t ga_rasterb_img_bytes(int32_t B, int32_t H, int32_t W) { return carve_img(nullptr, make_dims(B, 0, H, W)).total; }
+extern "C" size_t ga_rasterb_binning_bytes(int32_t B, int32_t H, int32_t W, int64_t capacity)
+{
+    return carve_bin(nullptr, capacity, make_dims(B, 0, H, W)).total;
+}
+extern "C" size_t ga_rasterb_bwd_scratch_bytes(int32_t B, int32_t P) { return bwd_scratch_bytes((size_t)B * (size_t)(P > 0 ? P : 0)); }
+extern "C" const int32_t *ga_rasterb_status(int32_t B, int32_t H, int32_t W, const void *img)
+{
+    return carve_img(const_cast<void *>(img), make_dims(B, 0, H, W)).status;
+}
+
+namespace ga {
+namespace {
+__global__ void stamp_serial_kernel(int32_t *status, const int32_t *serial) { status[kStatusInts - 1] = *serial; }
+}  // namespace
+}  // namespace ga
+
+// Copies the 16 status words (the caller's serial number stamped into word 15) to pinned host memory behind the forward, on
+// `stream`.  Plain cudaMemcpyAsync: capturable in a CUDA graph, no event involved — the host recognises a fresh copy by its serial.
+extern "C" int ga_rasterb_status_to_host(int32_t B, int32_t H, int32_t W, void *img, const int32_t *serial_dev, int32_t *host16,
+                                         void *stream_)
+{
+    if (int rc = check_dims(B, 0, H, W)) return rc;
+    GA_REQUIRE(img && serial_dev && host16, "NULL pointer argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    int32_t *status = carve_img(img, make_dims(B, 0, H, W)).status;
+    stamp_serial_kernel<<<1, 1, 0, stream>>>(status, serial_dev);
+    GA_CHECK_LAUNCH("stamp_serial_kernel");
+    GA_CHECK_CUDA(cudaMemcpyAsync(host16, status, sizeof(int32_t) * kStatusInts, cudaMemcpyDeviceToHost, stream));
     return GA_OK;
 }
 
-extern "C" int ga_raster_views(const GaRasterSettings *s, const void *geom, const void *binning, const void *img,
-                               int64_t R, GaRasterViews *out)
+extern "C" int ga_rasterb_forward(const GaRasterBatchDesc *bd, const float *cams, const float *bg, const float *means3D,
+                                  const float *colors, const float *scales, const float *rotations, const float *opacities,
+                                  void *geom, void *img, void *binning, int32_t *radii, float *out_color, void *stream_)
 {
-    if (int rc = check_settings(s)) return rc;
+    if (int rc = check_batch(bd)) return rc;
+    GA_REQUIRE(cams && bg && img && binning && out_color, "NULL pointer argument");
+    GA_REQUIRE(bd->P == 0 || (means3D && colors && scales && rotations && opacities && geom && radii), "NULL pointer argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const Dims d = make_dims(bd->B, bd->P, bd->H, bd->W);
+    GeomViews g = carve_geom(geom, (size_t)d.B * d.P);
+    ImgViews iv = carve_img(img, d);
+    BinViews bv = carve_bin(binning, bd->capacity, d);
+    const CamSrc cam{cams, cams + 16, cams + 32, kCamStride, 0.f, 0.f};
+    const FwdArgs a{means3D, colors, scales, rotations, opacities, bg, bd->rot_stride, bd->opac_stride, bd->scale_modifier};
+    if (int rc = launch_preprocess(d, cam, a, bd->capacity, g, iv, radii, stream)) return rc;
+    return launch_binning_and_render(d, a, bd->capacity, g, iv, bv, out_color, stream);
+}
+
+extern "C" int ga_rasterb_backward(const GaRasterBatchDesc *bd, const float *cams, const float *bg, const float *means3D,
+                                   const float *colors, const float *scales, const float *rotations, const int32_t *radii,
+                                   const void *geom, const void *img, const void *binning, const float *dL_dout, void *scratch,
+                                   float *d_means3D, float *d_colors, float *d_scales, float *d_rotations, float *d_opacities,
+                                   float *d_means2D, void *stream_)
+{
+    if (int rc = check_batch(bd)) return rc;
+    if (bd->P == 0) return GA_OK;
+    GA_REQUIRE(cams && bg && means3D && colors && scales && rotations && radii && geom && img && binning && dL_dout && scratch &&
+                   d_means3D && d_colors && d_scales,
+               "NULL pointer argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const Dims d = make_dims(bd->B, bd->P, bd->H, bd->W);
+    const CamSrc cam{cams, cams + 16, cams + 32, kCamStride, 0.f, 0.f};
+    const BwdArgs a{means3D, colors, scales, rotations, bg, dL_dout, bd->rot_stride, bd->scale_modifier, d_means3D, d_colors, d_scales,
+                    d_rotations, d_opacities, d_means2D};
+    return launch_backward(d, cam, a, radii, carve_geom(const_cast<void *>(geom), (size_t)d.B * d.P), carve_img(const_cast<void *>(img), d),
+                           carve_bin(const_cast<void *>(binning), bd->capacity, d), scratch, stream);
+}
+
+extern "C" int ga_raster_views(int32_t B, int32_t P, int32_t H, int32_t W, int64_t capacity, const void *geom, const void *binning,
+                               const void *img, GaRasterViews *out)
+{
+    if (int rc = check_dims(B, P, H, W)) return rc;
     GA_REQUIRE(out, "out is NULL");
     memset(out, 0, sizeof(*out));
+    const Dims d = make_dims(B, P, H, W);
     if (geom) {
-        GeomViews g = carve_geom(const_cast<void *>(geom), s->P);
+        GeomViews g = carve_geom(const_cast<void *>(geom), (size_t)B * P);
         out->depth = g.depth; out->xy = reinterpret_cast<const float *>(g.xy);
         out->conic_opacity = reinterpret_cast<const float *>(g.conic_o); out->cov3d = g.cov3d;
-        out->tiles_touched = g.tiles; out->offsets = g.offsets; out->rect = reinterpret_cast<const uint16_t *>(g.rect);
+        out->tiles_touched = g.tiles; out->rect = reinterpret_cast<const uint16_t *>(g.rect);
     }
-    if (binning && R > 0) {
-        BinViews b = carve_bin(const_cast<void *>(binning), R, s->H, s->W);
-        out->keys_unsorted = b.keys_unsorted; out->keys_sorted = b.keys;
-        out->vals_unsorted = b.vals_unsorted; out->vals_sorted = b.vals;
+    if (binning) {
+        BinViews bv = carve_bin(const_cast<void *>(binning), capacity, d);
+        out->point_list = bv.point_list;
     }
     if (img) {
-        ImgViews iv = carve_img(const_cast<void *>(img), s->H, s->W);
+        ImgViews iv = carve_img(const_cast<void *>(img), d);
         out->final_T = iv.final_T; out->n_contrib = iv.n_contrib; out->ranges = reinterpret_cast<const uint32_t *>(iv.ranges);
+        out->tile_count = iv.count; out->status = iv.status;
     }
     return GA_OK;
 }

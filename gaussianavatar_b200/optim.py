@@ -14,6 +14,7 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.grad_scale = 1.0
+        self.skip_flag = None      # device int32 tensor: a non-zero word makes the update a no-op (rasterizer overflow guard)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -34,6 +35,7 @@ class FusedAdam(torch.optim.Optimizer):
                 s["step"] = int(s["step"]) + 1
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
                 _lib.check(L.ga_adam_step(p.numel(), ptr(p), ptr(g), ptr(s["exp_avg"]), ptr(s["exp_avg_sq"]), float(group["lr"]),
-                                          float(b1), float(b2), float(group["eps"]), s["step"], float(self.grad_scale), st),
+                                          float(b1), float(b2), float(group["eps"]), s["step"], float(self.grad_scale),
+                                          ptr(self.skip_flag), st),
                            "ga_adam_step")
         return None

@@ -6,6 +6,8 @@ the shared feature-net / geo_feature gradients).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -34,9 +36,18 @@ def allreduce_gradients(grads, group=None):
         w.wait()
 
 
+class _StepGraph:
+    """One captured forward + loss + backward of a stage-1 step and its static input / output tensors."""
+    __slots__ = ("graph", "idx", "gt", "cams", "loss", "g_flat", "g_geo", "capacity", "plan", "states", "launches")
+
+
 class Stage1Trainer:
-    def __init__(self, model, fused_adam: bool = True, process_group=None):
+    def __init__(self, model, fused_adam: bool = True, process_group=None, use_graph=None):
         self.model = model
+        # whole-step CUDA graph (forward + loss + backward in ONE launch; all-reduce and Adam follow eagerly): on unless GA_STEP_GRAPH=0
+        self.use_graph = (os.environ.get("GA_STEP_GRAPH", "1") != "0") if use_graph is None else bool(use_graph)
+        self._graphs = {}
+        self.replayed_launches = 0      # kernels of this library launched through graph replays (ga_launch_count sees only eager launches)
         self.opt = model.opt_parms
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.group = process_group
@@ -59,21 +70,173 @@ class Stage1Trainer:
     epoch_start = 0    # train.py:38-45: 0 unless resuming from a checkpoint
 
     def sync_gradients(self):
-        """All-reduce(sum) of the shared parameters' gradients; the 1/world factor is folded into the Adam kernel.
-        Pose / transl embedding rows are per-frame and stay rank-local (sparse grads)."""
+        """Data parallelism: ONE all-reduce(sum) per step over a flat bucket [net.flat.grad | geo_feature.grad | overflow flag]
+        (6.2 MB), issued asynchronously on NCCL's stream; the compute stream waits for it in-stream (the host does not), the
+        1/world factor is folded into the Adam kernel and the gradients Adam reads are the bucket's views.  The last word
+        carries the batched rasterizer's overflow flag, so that every rank skips (and later re-runs) a step any rank could not
+        fit.  Pose / transl embedding rows are per-frame and stay rank-local (sparse grads)."""
         if self.world == 1:
             return
         m = self.model
-        allreduce_gradients([m.net.flat.grad, m.geo_feature.grad], self.group)
+        gf, gg = m.net.flat.grad, m.geo_feature.grad
+        n1, n2 = gf.numel(), gg.numel()
+        bk = getattr(self, "_bucket", None)
+        if bk is None or bk.numel() != n1 + n2 + 1:
+            bk = self._bucket = torch.zeros(n1 + n2 + 1, dtype=torch.float32, device=gf.device)
+            self._skip = torch.zeros(1, dtype=torch.int32, device=gf.device)
+            self._flag_host = torch.zeros(1, dtype=torch.float32).pin_memory() if gf.is_cuda else torch.zeros(1)
+            self._flag_event = torch.cuda.Event() if gf.is_cuda else None
+        bk[:n1].copy_(gf.reshape(-1))
+        bk[n1:n1 + n2].copy_(gg.reshape(-1))
+        plan = getattr(m, "_last_plan", None)
+        if plan is not None:
+            bk[n1 + n2:].copy_(plan.status_dev[1:2])
+        else:
+            bk[n1 + n2:].zero_()
+        work = dist.all_reduce(bk, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        work.wait()                                   # stream-level wait on CUDA; a host wait only with gloo (CPU tests)
+        m.net.flat.grad = bk[:n1].view_as(gf)
+        m.geo_feature.grad = bk[n1:n1 + n2].view_as(gg)
+        self._skip.copy_(bk[n1 + n2:] != 0)
+        self._flag_host.copy_(bk[n1 + n2:], non_blocking=True)
+        if self._flag_event is not None:
+            self._flag_event.record()
+
+    def _step_fitted(self) -> bool:
+        """Did the previous step fit the rasterizer's binning buffer — on every rank?  (Grows this rank's buffer if it did not.)"""
+        ok = self.model.raster_ok(wait=True)
+        if self.world > 1 and getattr(self, "_flag_event", None) is not None:
+            self._flag_event.synchronize()
+            ok = ok and float(self._flag_host[0]) == 0.0
+        return ok
 
     def step(self, batch, iteration: int, epoch: int = 0):
+        """One optimisation step.  The batched rasterizer never makes the host wait for the device: whether the step's binning
+        buffer was large enough is known one step later (the device flag also turns that step's Adam launches into no-ops), so
+        an overflowed step is detected here, before the next one, and simply run again with the grown buffer."""
+        prev = getattr(self, "_prev", None)
+        if prev is not None and not self._step_fitted():
+            self._undo_host_step(prev[2])
+            self._step_once(*prev)
+            if not self._step_fitted():
+                raise RuntimeError("batched rasterizer: binning buffer overflowed twice in a row")
+        self._prev = (batch, iteration, epoch)
+        return self._step_once(batch, iteration, epoch)
+
+    def finish(self):
+        """Settle the last step (re-run it if its binning buffer overflowed)."""
+        prev, self._prev = getattr(self, "_prev", None), None
+        if prev is not None and not self._step_fitted():
+            self._undo_host_step(prev[2])
+            self._step_once(*prev)
+            if not self._step_fitted():
+                raise RuntimeError("batched rasterizer: binning buffer overflowed twice in a row")
+
+    def _undo_host_step(self, epoch):
+        """Host-side bookkeeping of a step the device skipped (Adam step counts, lr schedule)."""
         m = self.model
-        loss, _ = self.loss(batch, iteration, epoch)
-        m.zero_grad(epoch)
-        loss.backward()
+        for st in m.optimizer.state.values():
+            if "step" in st:
+                st["step"] = st["step"] - 1
+        m.scheduler.last_epoch -= 1
+        m.scheduler._step_count -= 1
+        for g, lr in zip(m.optimizer.param_groups, m.scheduler._get_closed_form_lr() if hasattr(m.scheduler, "_get_closed_form_lr") else m.scheduler.get_last_lr()):
+            g["lr"] = lr
+
+    # ---- whole-step CUDA graph -------------------------------------------------------------------------------------------------
+    def _graph_applicable(self, batch, iteration, epoch) -> bool:
+        """The captured step holds no host-dependent value: the scale ramp is over (iteration >= 1000, avatar_model.py:316-319), pose
+        optimisation is inactive (its sparse embedding gradients are then never read, avatar_model.py:261-270) and the frames share
+        one image size."""
+        m = self.model
+        img = batch.get("original_image")
+        return (self.use_graph and isinstance(m.optimizer, FusedAdam) and iteration >= 1000 and epoch <= self.opt.pose_op_start_iter
+                and torch.is_tensor(img) and img.is_cuda and img.shape[0] <= 8 and os.environ.get("GA_RASTER_BATCHED", "1") != "0"
+                and m._uniform_frames(batch, img.shape[0]))
+
+    def _capture(self, batch, iteration, epoch, key):
+        m = self.model
+        dev = m.device
+        B = batch["original_image"].shape[0]
+        G = _StepGraph()
+        G.idx = batch["pose_idx"].to(dev).clone()
+        G.gt = batch["original_image"].float().contiguous().clone()
+        G.cams = m._batch_cameras(batch, B, dev).clone()
+        sb = dict(batch)
+        sb.update(pose_idx=G.idx, original_image=G.gt, _cams=G.cams, height=m._scalar_list(batch["height"], B),
+                  width=m._scalar_list(batch["width"], B))
+        m._detach_pose = True
+        run_backup = m.net.bn_running.clone()
+        states = [(st, st.num_batches_tracked) for st in m.net._states.values()]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up off the capture: allocator pools, lazy one-time setup in the library
+            for _ in range(2):
+                loss, _ = self.loss(sb, iteration, epoch)
+                m.optimizer.zero_grad(set_to_none=True)
+                loss.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        if not m.raster_ok(wait=True):                      # the warm-up found the binning buffer too small: it has been grown
+            pass
+        m.optimizer.zero_grad(set_to_none=True)
+        from . import _lib
+        G.graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(G.graph):
+            loss, _ = self.loss(sb, iteration, epoch)
+            loss.backward()
+        G.launches = _lib.launch_count() - l0
+        G.loss = loss.detach()
+        G.g_flat, G.g_geo = m.net.flat.grad, m.geo_feature.grad
+        G.plan = m._last_plan
+        G.capacity = G.plan.capacity
+        m.net.bn_running.copy_(run_backup)                  # warm-up and capture must not count as training iterations
+        G.states = [st for st, n in states if st.num_batches_tracked != n] or [st for st in m.net._states.values()
+                                                                                 if not any(st is s0 for s0, _ in states)]
+        for st in m.net._states.values():
+            st.num_batches_tracked = 0
+        for st, n in states:
+            st.num_batches_tracked = n
+        m._detach_pose = False
+        self._graphs[key] = G
+        return G
+
+    def _step_graphed(self, batch, iteration, epoch):
+        m, o = self.model, self.opt
+        B = batch["original_image"].shape[0]
+        wdecay_rgl = adjust_loss_weights(o.lambda_rgl, epoch, mode="decay", start=self.epoch_start, every=20)
+        key = (B, tuple(batch["original_image"].shape[-2:]), float(wdecay_rgl))
+        G = self._graphs.get(key)
+        if G is not None and G.capacity != G.plan.capacity:      # the rasterizer's buffers were re-allocated: the graph points at freed memory
+            G = None
+        if G is None:
+            G = self._capture(batch, iteration, epoch, key)
+        G.idx.copy_(batch["pose_idx"], non_blocking=True)
+        G.gt.copy_(batch["original_image"], non_blocking=True)
+        G.cams.copy_(m._batch_cameras(batch, B, m.device))
+        G.plan.bump_serial()
+        G.plan.pending = True
+        m._last_plan = G.plan
+        G.graph.replay()
+        self.replayed_launches += G.launches
+        for st in G.states:
+            st.num_batches_tracked += 1
+        m.net.flat.grad, m.geo_feature.grad = G.g_flat, G.g_geo
+        return G.loss
+
+    def _step_once(self, batch, iteration: int, epoch: int = 0):
+        m = self.model
+        if self._graph_applicable(batch, iteration, epoch):
+            loss = self._step_graphed(batch, iteration, epoch)
+        else:
+            loss, _ = self.loss(batch, iteration, epoch)
+            m.zero_grad(epoch)
+            loss.backward()
         self.sync_gradients()
         if isinstance(m.optimizer, FusedAdam):
             m.optimizer.grad_scale = 1.0 / self.world
+            plan = getattr(m, "_last_plan", None)
+            m.optimizer.skip_flag = self._skip if self.world > 1 else (plan.status_dev[1:2] if plan is not None else None)
         elif self.world > 1:
             for g in (m.net.flat.grad, m.geo_feature.grad):
                 g.div_(self.world)

@@ -89,7 +89,8 @@ class Stage1Workload:
 
     def device_batch(self, ids):
         """Batch dict (scene/dataset_mono.py:238-255 keys) with inputs already resident in HBM."""
-        idx = torch.tensor(ids, device=self.device)
+        # pinned staging + asynchronous copy: a pageable `torch.tensor(ids, device=...)` would make the host wait for the whole stream
+        idx = torch.tensor(ids).pin_memory().to(self.device, non_blocking=True)
         return dict(pose_idx=idx, original_image=self.gt_dev[idx], **self.camera_fields(len(ids)))
 
     def host_batch(self, ids):

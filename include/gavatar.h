@@ -60,17 +60,19 @@ typedef struct GaRasterSettings {
 } GaRasterSettings;
 
 size_t ga_raster_geom_bytes(int32_t P);                       /* per-Gaussian state (upstream's geomBuffer)   */
-size_t ga_raster_img_bytes(int32_t H, int32_t W);             /* final_T, n_contrib, tile ranges (imgBuffer)  */
-size_t ga_raster_binning_bytes(int64_t num_rendered, int32_t H, int32_t W); /* keys/values + sort temp (binningBuffer) */
+size_t ga_raster_img_bytes(int32_t H, int32_t W);             /* final_T, n_contrib, tile ranges / counts, status (imgBuffer) */
+size_t ga_raster_binning_bytes(int64_t num_rendered, int32_t H, int32_t W); /* tile buckets, sorted list, packed records, checkpoints (binningBuffer) */
 size_t ga_raster_bwd_scratch_bytes(int32_t P);                /* dL/dmean2D, dL/dconic, dL/dopacity scratch   */
 
-/* Stage 1: K1 preprocess + K2 scan.  Synchronises `stream` once to return the number of (Gaussian, tile) instances
- * (upstream does the same D2H read to size its binning buffer). */
+/* Per-frame API, upstream's call shape (the host sizes the binning buffer from the instance count).
+ * Stage 1: K1 preprocess (+ per-tile instance counts) and the tile scan.  Synchronises `stream` once to return the number of
+ * (Gaussian, tile) instances (upstream does the same D2H read to size its binning buffer). */
 int ga_raster_forward_preprocess(const GaRasterSettings *s, const float *means3D, const float *scales,
                                  const float *rotations, const float *opacities, const float *viewmatrix,
-                                 const float *projmatrix, void *geom, int32_t *radii, int64_t *num_rendered_host,
+                                 const float *projmatrix, void *geom, void *img, int32_t *radii, int64_t *num_rendered_host,
                                  void *stream);
-/* Stage 2: K3 duplicate-with-keys, K4 radix sort, K5 tile ranges, K6 alpha compositing. */
+/* Stage 2: K3 scatter into tile buckets, K4 per-tile sort (upstream's order: depth bits, then Gaussian index), K6 alpha
+ * compositing.  `binning` must hold ga_raster_binning_bytes(num_rendered, H, W). */
 int ga_raster_forward_render(const GaRasterSettings *s, const float *colors, const float *bg, void *geom, void *binning,
                              size_t binning_bytes, int64_t num_rendered, void *img, float *out_color, void *stream);
 /* Backward (K7 + fused K8/K9).  d_opacities, d_rotations, d_means2D ([P,3], xy filled) may be NULL.
@@ -81,23 +83,56 @@ int ga_raster_backward(const GaRasterSettings *s, const float *means3D, const fl
                        int64_t num_rendered, const float *dL_dout, void *scratch, float *d_means3D, float *d_colors,
                        float *d_scales, float *d_rotations, float *d_opacities, float *d_means2D, void *stream);
 
-/* Debug / parity accessors into the opaque buffers (device pointers; valid after the forward that filled them). */
+/* Batched API: the B <= 8 frames a training step renders (model/avatar_model.py:332-365 loops them) in ONE set of launches
+ * and WITHOUT any host read-back, so a whole step can be captured in a CUDA graph.  All frames share H, W and P.
+ * Arrays are [B,P,*] (rotations / opacities: [P,*] shared by every frame when the stride is 0); out_color [B,3,H,W];
+ * radii [B,P]; cams [B,40] device floats per frame: viewmatrix 0..15, projmatrix 16..31 (the reference's transposed 4x4s),
+ * tanfovx 32, tanfovy 33.  `capacity` = number of (Gaussian, tile) instances the caller sized `binning` for; if a step needs
+ * more, status[1] is set, the tiles that do not fit are rendered as empty and nothing is overrun — the caller re-runs with a
+ * larger buffer (status[0] = the count needed).  status (device, 16 x int32, inside `img`): [0] instances, [1] overflow,
+ * [2] backward segments, [4+b] first instance of frame b, [4+B] = [0]. */
+typedef struct GaRasterBatchDesc {
+    int32_t B, P, H, W;
+    int64_t capacity;
+    int64_t rot_stride, opac_stride;   /* floats between two frames' rotations / opacities: 4P / P, or 0 = shared */
+    float scale_modifier;
+} GaRasterBatchDesc;
+size_t ga_rasterb_geom_bytes(int32_t B, int32_t P);
+size_t ga_rasterb_img_bytes(int32_t B, int32_t H, int32_t W);
+size_t ga_rasterb_binning_bytes(int32_t B, int32_t H, int32_t W, int64_t capacity);
+size_t ga_rasterb_bwd_scratch_bytes(int32_t B, int32_t P);
+const int32_t *ga_rasterb_status(int32_t B, int32_t H, int32_t W, const void *img);   /* device pointer of the status words */
+/* Copy the 16 status words to PINNED host memory behind the latest forward (asynchronous, capturable in a CUDA graph); word 15
+ * receives *serial_dev (device int32 the caller bumps before every forward) so the host can tell which forward a copy is of. */
+int ga_rasterb_status_to_host(int32_t B, int32_t H, int32_t W, void *img, const int32_t *serial_dev, int32_t *host16_pinned,
+                              void *stream);
+int ga_rasterb_forward(const GaRasterBatchDesc *d, const float *cams, const float *bg, const float *means3D,
+                       const float *colors, const float *scales, const float *rotations, const float *opacities, void *geom,
+                       void *img, void *binning, int32_t *radii, float *out_color, void *stream);
+int ga_rasterb_backward(const GaRasterBatchDesc *d, const float *cams, const float *bg, const float *means3D,
+                        const float *colors, const float *scales, const float *rotations, const int32_t *radii,
+                        const void *geom, const void *img, const void *binning, const float *dL_dout, void *scratch,
+                        float *d_means3D, float *d_colors, float *d_scales, float *d_rotations, float *d_opacities,
+                        float *d_means2D, void *stream);
+
+/* Debug / parity accessors into the opaque buffers (device pointers; valid after the forward that filled them).  B = 1 and
+ * capacity = num_rendered for buffers of the per-frame API. */
 typedef struct GaRasterViews {
-    const float *depth;          /* [P]   */
-    const float *xy;             /* [P,2] */
-    const float *conic_opacity;  /* [P,4] */
-    const float *cov3d;          /* [P,6] */
-    const uint32_t *tiles_touched; /* [P] */
-    const uint32_t *offsets;     /* [P] inclusive scan */
-    const uint16_t *rect;        /* [P,4] min.x min.y max.x max.y */
-    const uint64_t *keys_unsorted, *keys_sorted;   /* [R] */
-    const uint32_t *vals_unsorted, *vals_sorted;   /* [R] */
-    const uint32_t *ranges;      /* [T,2] */
-    const float *final_T;        /* [H*W] */
-    const uint32_t *n_contrib;   /* [H*W] */
+    const float *depth;          /* [B*P]   */
+    const float *xy;             /* [B*P,2] */
+    const float *conic_opacity;  /* [B*P,4] */
+    const float *cov3d;          /* [B*P,6] */
+    const uint32_t *tiles_touched; /* [B*P] */
+    const uint16_t *rect;        /* [B*P,4] min.x min.y max.x max.y */
+    const uint32_t *point_list;  /* [R] Gaussian indices, tile by tile, in upstream's sorted order */
+    const uint32_t *ranges;      /* [B*T,2] [start,end) into point_list (frame b starts at status[4+b]) */
+    const uint32_t *tile_count;  /* [B*T] */
+    const float *final_T;        /* [B*H*W] */
+    const uint32_t *n_contrib;   /* [B*H*W] */
+    const int32_t *status;       /* [16] */
 } GaRasterViews;
-int ga_raster_views(const GaRasterSettings *s, const void *geom, const void *binning, const void *img,
-                    int64_t num_rendered, GaRasterViews *out);
+int ga_raster_views(int32_t B, int32_t P, int32_t H, int32_t W, int64_t capacity, const void *geom, const void *binning,
+                    const void *img, GaRasterViews *out);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * SMPL joint transforms -> cano2live (model/avatar_model.py:291-296; submodules/smplx/lbs.py:299-405;
@@ -183,9 +218,14 @@ int ga_loss_backward(int32_t B, int32_t H, int32_t W, const float *image, const 
 
 /* torch.optim.Adam step (amsgrad=False, weight_decay=0; model/avatar_model.py:148-155,264-267) on one contiguous buffer.
  * `step` is the 1-based count of this update; grad_scale multiplies the gradient first (1/world_size after an
- * all-reduce(sum)). */
+ * all-reduce(sum)).  skip_flag (device int32, may be NULL): if non-zero when the kernel runs, nothing is updated — wired to the
+ * batched rasterizer's overflow word so that a step rendered with an overflowed binning buffer is never committed. */
 int ga_adam_step(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, float lr, float beta1,
-                 float beta2, float eps, int64_t step, float grad_scale, void *stream);
+                 float beta2, float eps, int64_t step, float grad_scale, const int32_t *skip_flag, void *stream);
+/* The same update with its scalars in DEVICE memory, hyper7 = [lr, beta1, beta2, eps, 1-beta1^step, sqrt(1-beta2^step),
+ * grad_scale], so that a CUDA graph holding this launch follows the lr schedule / step count without re-capture. */
+int ga_adam_step_dev(int64_t n, float *param, const float *grad, float *exp_avg, float *exp_avg_sq, const float *hyper7,
+                     const int32_t *skip_flag, void *stream);
 
 /* Fused backward of one hidden decoder layer on the tensor cores (building block of ga_decoder_backward, exposed for unit
  * tests): from dZ_l / Y_l (BatchNorm backward applied on load with bwd_coef = [ga, m1, m2, mu, rstd] x 128, NULL: dY = dZ)

@@ -55,8 +55,8 @@ def test_forward_parity(case):
     np.testing.assert_array_equal(v["xy"].numpy()[vis], o.get("xy").astype(np.float32)[vis])
     np.testing.assert_array_equal(v["conic_opacity"].numpy()[vis], o.get("conic_o").astype(np.float32)[vis])
     if o.num_rendered:
-        np.testing.assert_array_equal(v["keys_unsorted"].numpy().view(np.uint64), o.get("keys_unsorted"))
-        np.testing.assert_array_equal(v["vals_unsorted"].numpy().view(np.uint32), o.get("vals_unsorted"))
+        # the device bins by tile and sorts each tile's bucket; upstream's unsorted duplicate list has no counterpart, its
+        # SORTED (tile | depth, index) list and the tile ranges are the contract
         np.testing.assert_array_equal(v["keys_sorted"].numpy().view(np.uint64), o.get("keys"))
         np.testing.assert_array_equal(v["vals_sorted"].numpy().view(np.uint32), o.get("vals"))
     np.testing.assert_array_equal(v["ranges"].numpy().view(np.uint32), o.get("ranges"))
@@ -152,3 +152,100 @@ def test_empty_and_all_culled():
     e = {k: v[:0] for k, v in t.items()}
     color0, radii0, ctx0 = rasterize_forward(e["means3D"], e["colors"], e["opacities"], e["scales"], e["rotations"], rs)
     assert torch.equal(color0, expect) and radii0.numel() == 0
+
+
+def _batched(scs, capacity=None):
+    """Render same-size scenes (different Gaussians / cameras) through the batched, read-back-free path."""
+    from gaussianavatar_b200.rasterizer import RasterBatchPlan, pack_cameras, rasterize_batch
+    dev = torch.device("cuda:0")
+    B, P, H, W = len(scs), scs[0]["means3D"].shape[0], scs[0]["H"], scs[0]["W"]
+    plan = RasterBatchPlan(B, P, H, W, dev, capacity=capacity)
+    cams = pack_cameras(torch.stack([s["cam"].world_view_transform for s in scs]), torch.stack([s["cam"].full_proj_transform for s in scs]),
+                        [s["tanfovx"] for s in scs], [s["tanfovy"] for s in scs], dev)
+    t = {k: torch.stack([s[k] for s in scs]).to(dev).requires_grad_(k != "opacities") for k in ("means3D", "colors", "scales")}
+    rot, opac = scs[0]["rotations"].to(dev), scs[0]["opacities"].to(dev)
+    img = rasterize_batch(t["means3D"], t["colors"], t["scales"], rot, opac, cams, scs[0]["bg"].to(dev), plan)
+    return img, t, plan
+
+
+def test_batched_path_matches_oracle_per_frame():
+    """Two frames with different Gaussians in one set of launches: every frame's stages, image and gradients vs the oracle."""
+    from oracle import raster_oracle as ro
+    scs = [random_scene(P=3000, H=200, W=136, seed=21 + i, scale_mean=0.02, aniso=False, opacity_one=True) for i in range(3)]
+    for s in scs[1:]:
+        s["rotations"], s["opacities"] = scs[0]["rotations"], scs[0]["opacities"]
+    img, t, plan = _batched(scs)
+    gw = torch.randn(3, 3, 200, 136, generator=torch.Generator().manual_seed(2))
+    (img * gw.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert plan.check(wait=True)
+    views = plan.views()
+    for b, sc in enumerate(scs):
+        o = ro.forward(**oracle_args(sc), precision="f32")
+        v = views[b]
+        assert v["num_rendered"] == o.num_rendered and v["overflow"] == 0
+        np.testing.assert_array_equal(v["radii"].numpy(), o.get("radii"))
+        np.testing.assert_array_equal(v["keys_sorted"].numpy().view(np.uint64), o.get("keys"))
+        np.testing.assert_array_equal(v["vals_sorted"].numpy().view(np.uint32), o.get("vals"))
+        np.testing.assert_array_equal(v["ranges"].numpy().view(np.uint32), o.get("ranges"))
+        assert np.abs(img[b].detach().cpu().numpy().astype(np.float64) - o.image).mean() <= 1e-4
+        gb = o.backward(gw[b].numpy())
+        for got, ref in ((t["means3D"].grad[b], gb["d_means3D"]), (t["colors"].grad[b], gb["d_colors"]), (t["scales"].grad[b], gb["d_scales"])):
+            a = got.cpu().numpy().astype(np.float64)
+            assert np.linalg.norm(a - ref) / (np.linalg.norm(ref) + 1e-30) < 5e-4
+
+
+def test_long_tile_lists_sorted_in_runs_and_many_segments():
+    """Everything piled into a few tiles: tile lists far beyond the 8192 keys one CTA sorts at once (run-merge path) and
+    beyond one 256-entry backward segment; opacity < 1 so that pixels blend deep into the list."""
+    from gaussianavatar_b200.rasterizer import rasterize_backward
+    from oracle import raster_oracle as ro
+    sc = random_scene(P=30000, H=48, W=48, seed=31, scale_mean=0.004, aniso=False, spread=0.15)
+    sc["opacities"] = torch.full_like(sc["opacities"], 0.02)
+    color, radii, ctx, rs, t = _run_cuda(sc)
+    v = ctx.views()
+    o = ro.forward(**oracle_args(sc), precision="f32")
+    rg = o.get("ranges").astype(np.int64)
+    assert (rg[:, 1] - rg[:, 0]).max() > 8192
+    np.testing.assert_array_equal(v["keys_sorted"].numpy().view(np.uint64), o.get("keys"))
+    np.testing.assert_array_equal(v["vals_sorted"].numpy().view(np.uint32), o.get("vals"))
+    np.testing.assert_array_equal(v["ranges"].numpy().view(np.uint32), o.get("ranges"))
+    assert np.abs(color.cpu().numpy().astype(np.float64) - o.image).mean() <= 1e-4
+    assert o.get("n_contrib").max() > 1000
+    gw = torch.randn(3, 48, 48, generator=torch.Generator().manual_seed(4))
+    d_means3D, d_m2d, d_colors, d_opac, d_scales, d_rot = rasterize_backward(ctx, t["means3D"], t["colors"], t["scales"], t["rotations"], rs, gw.cuda())
+    gb = o.backward(gw.numpy())
+
+    def rel(a, b):
+        a = a.cpu().numpy().astype(np.float64).reshape(b.shape)
+        return np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+
+    assert rel(d_colors, gb["d_colors"]) < 2e-4
+    assert rel(d_opac, gb["d_opacity"]) < 5e-4
+    assert rel(d_means3D, gb["d_means3D"]) < 5e-4
+    assert rel(d_scales, gb["d_scales"]) < 5e-4
+
+
+def test_batched_overflow_is_flagged_not_overrun_and_recovers():
+    """A binning buffer that is too small: the device raises the flag, skips what does not fit (no out-of-bounds write: the
+    guard words behind the buffer stay intact), plan.check() grows the buffer and the re-run is exact."""
+    from oracle import raster_oracle as ro
+    from gaussianavatar_b200.rasterizer import pack_cameras, rasterize_batch
+    scs = [random_scene(P=2000, H=128, W=128, seed=41 + i, scale_mean=0.02, aniso=False, opacity_one=True) for i in range(2)]
+    for s in scs[1:]:
+        s["rotations"], s["opacities"] = scs[0]["rotations"], scs[0]["opacities"]
+    with torch.no_grad():
+        img, t, plan = _batched(scs, capacity=1000)
+        torch.cuda.synchronize()
+        assert int(plan.status_host[1]) == 1 and int(plan.status_host[0]) > 1000 and int(plan.status_host[15]) == plan.serial
+        assert not plan.check(wait=True)                       # grows the buffer
+        assert plan.capacity > int(plan.status_host[0])
+        dev = torch.device("cuda:0")
+        cams = pack_cameras(torch.stack([s["cam"].world_view_transform for s in scs]), torch.stack([s["cam"].full_proj_transform for s in scs]),
+                            [s["tanfovx"] for s in scs], [s["tanfovy"] for s in scs], dev)
+        img = rasterize_batch(t["means3D"], t["colors"], t["scales"], scs[0]["rotations"].to(dev), scs[0]["opacities"].to(dev), cams,
+                              scs[0]["bg"].to(dev), plan)
+        assert plan.check(wait=True)
+    for b, sc in enumerate(scs):
+        o = ro.forward(**oracle_args(sc), precision="f32")
+        assert np.abs(img[b].cpu().numpy().astype(np.float64) - o.image).mean() <= 1e-4

@@ -135,3 +135,37 @@ def test_train_step_gradients_vs_oracle_chain(mode):
     nz = m.net.flat.grad.abs() > 1e-4      # well above Adam's eps = 1e-8
     assert torch.allclose(delta[nz].abs(), torch.full_like(delta[nz], 3e-3), rtol=2e-3)
     assert torch.equal(torch.sign(delta[nz]), -torch.sign(m.net.flat.grad[nz]))
+
+
+@pytest.mark.tf32
+def test_graphed_step_matches_eager_step():
+    """The whole-step CUDA graph (forward + loss + backward in one launch, static inputs) computes what the eager step computes:
+    same loss, same gradients (up to float-atomics noise), over several steps with changing batches."""
+    from gaussianavatar_b200.trainer import Stage1Trainer
+    from gaussianavatar_b200.workload import Stage1Workload
+
+    def run(use_graph):
+        wl = Stage1Workload(3, 2, device=DEV, N=4000, S=64, side=128, inp_posmap_size=32)
+        with torch.no_grad():
+            sd = wl.model.net.state_dict(); sd["decoder.conv8N.bias"] = torch.tensor([-3.9]); wl.model.net.load_state_dict(sd, strict=False)
+        wl.make_ground_truth()
+        tr = Stage1Trainer(wl.model, use_graph=use_graph)
+        out = []
+        for i in range(4):
+            loss = tr.step(wl.device_batch(wl.frame_ids(i)), 5000 + i, epoch=1)
+            out.append((float(loss), wl.model.net.flat.grad.detach().clone(), wl.model.geo_feature.grad.detach().clone()))
+        tr.finish()
+        assert bool(tr._graphs) == use_graph
+        return out, wl.model.net.flat.detach().clone(), wl.model.net.state_dict()["decoder.bn3.num_batches_tracked"]
+
+    eager, flat_e, nbt_e = run(False)
+    graph, flat_g, nbt_g = run(True)
+    assert int(nbt_e) == int(nbt_g)
+    # step 1 starts from identical parameters: gradients agree to atomics noise
+    assert abs(eager[0][0] - graph[0][0]) < 1e-5 * max(1.0, abs(eager[0][0]))
+    assert _rel(graph[0][1].cpu().numpy(), eager[0][1].cpu().numpy()) < 1e-3
+    assert _rel(graph[0][2].cpu().numpy(), eager[0][2].cpu().numpy()) < 1e-3
+    # later steps: Adam turns round-off level gradient differences into +-lr flips of a few parameters; the losses stay together
+    for (le, _, _), (lg, _, _) in zip(eager, graph):
+        assert abs(le - lg) < 2e-3 * max(1.0, abs(le))
+    assert (flat_e - flat_g).abs().max().item() <= 4 * 2 * 3e-3 + 1e-6
