@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--frames-per-gpu", type=int, default=2, help="frames per step and GPU (reference batch_size=2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-4 (1 frame/GPU) and config-5 (novel-pose) side measurements")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -404,6 +405,103 @@ def main():
                        "algorithmic_bytes": cost["raster_fwd_bytes"], "ms_per_frame": raster_fwd_ms, "num_rendered": R,
                        "bwd_ms_per_frame": raster_bwd_ms, "peak_source": peaks["_source"]}
 
+    # ---- BASELINE configs 4 and 5 next to the headline ---------------------------------------------------
+    extra = {}
+    step_graph_used = bool(trainer.use_graph and trainer._graphs)
+    if not args.no_extra:
+        trainer.finish()
+        del trainer
+        wl.model._raster_plans = {}
+        torch.cuda.empty_cache()
+
+        def timed_loop(fn, n):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(n); e1.record()
+            barrier()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
+        # config 4 literally: ONE pose per GPU per step (8 poses / step over 8 GPUs), the decoder no longer amortised over 2 frames
+        wl4 = Stage1Workload(4, 1, device=dev)
+        wl4.make_ground_truth()
+        tr4 = Stage1Trainer(wl4.model, fused_adam=True)
+
+        def run4(n, start=[0]):
+            for i in range(n):
+                tr4.step(wl4.device_batch(wl4.frame_ids(start[0] + i, rank, world)), iteration0 + start[0] + i, epoch=1)
+            start[0] += n
+        run4(max(3, args.warmup))
+        ms4 = timed_loop(run4, args.steps)
+        tr4.finish()
+        extra["config4_one_pose_per_gpu"] = {"value": world * args.steps / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4 / args.steps,
+                                             "global_batch": world, "workload": "config4: 200000 Gaussians, 1024x1024, stage-1 train step, 1 frame/GPU/step"}
+        del tr4, wl4
+        torch.cuda.empty_cache()
+
+        # config 5: novel-pose rendering (render_novel_pose.py:12-33 -> AvatarModel.render_free_stage1), forward only, 500k Gaussians / 2048^2;
+        # an inference model evaluates the frame-invariant stage-1 net once (cached), per frame: SMPL -> LBS -> rasterizer
+        from gaussianavatar_b200.workload import load_poses
+        wl5 = Stage1Workload(5, 1, device=dev)
+        m5 = wl5.model
+        m5.cache_decoder = True
+        poses5, transl5, _ = load_poses(32)
+        pin = lambda t: t.contiguous().pin_memory()
+        host_frames = [(pin(poses5[i:i + 1]), pin(transl5[i:i + 1])) for i in range(poses5.shape[0])]
+        dev_frames = [(p.to(dev), t.to(dev)) for p, t in host_frames]
+        cam5 = wl5.camera_fields(1)
+        idx0 = torch.zeros(1, dtype=torch.long, device=dev)
+        out_host = torch.empty(1, 3, wl5.side, wl5.side).pin_memory()
+        m5.defer_raster_check = True
+
+        def run5(n, start=[0], e2e=False):
+            with torch.no_grad():
+                for i in range(n):
+                    f = (start[0] + i * world + rank) % len(dev_frames)
+                    if e2e:
+                        p, t = host_frames[f][0].to(dev, non_blocking=True), host_frames[f][1].to(dev, non_blocking=True)
+                    else:
+                        p, t = dev_frames[f]
+                    img = m5.render_free_stage1(dict(pose_idx=idx0, pose_data=p, transl_data=t, **cam5), 59400)
+                    if e2e:
+                        out_host.copy_(img, non_blocking=True)       # the frame goes back to the host (render_novel_pose.py:32 saves it)
+            start[0] += n * world
+            assert m5.raster_ok(wait=True), "binning buffer overflow during the timed novel-pose loop"
+        run5(4); run5(4)
+        n5 = max(args.steps, 20)
+        ms5 = timed_loop(run5, n5)
+        ms5e = timed_loop(lambda n: run5(n, e2e=True), n5)
+        plan5 = m5._last_plan
+        extra["config5_novel_pose"] = {"value": world * n5 / (ms5 * 1e-3), "unit": UNIT, "ms_per_frame": ms5 / n5,
+                                       "e2e": {"value": world * n5 / (ms5e * 1e-3), "unit": UNIT, "ms_per_frame": ms5e / n5,
+                                               "h2d_bytes_per_frame": 300, "d2h_bytes_per_frame": int(out_host.numel() * 4)},
+                                       "num_rendered": int(plan5.status_host[0]), "frames": n5,
+                                       "workload": f"config5: {wl5.N} Gaussians, UV {wl5.S}^2, {wl5.side}x{wl5.side}, novel-pose forward "
+                                                   "(decoder output cached across frames), 1 frame per GPU at a time"}
+        # per-stage kernel times of one novel-pose frame
+        _lib.profile(True); _lib.profile_report()
+        run5(5)
+        torch.cuda.synchronize()
+        p5 = _lib.profile_report(); _lib.profile(False)
+        extra["config5_novel_pose"]["kernel_ms_per_frame"] = {k: round(ms / 5, 4) for k, (n, ms) in sorted(p5.items(), key=lambda kv: -kv[1][1])}
+        T5 = ((wl5.side + 15) // 16) ** 2
+        R5 = int(plan5.status_host[0])
+        # algorithmic HBM bytes of the streaming stages of ONE frame: K1 reads 56 B / writes 44 B per Gaussian (+4 B per
+        # instance of tile-count atomics), K3 reads 12 B per Gaussian and writes 8 B per instance, K4 reads 8 B, gathers 40 B and writes
+        # 52 B per instance, K6 streams 48 B per instance per sub-tile pass (L1/L2 resident) and writes 36 B per pixel
+        stage_bytes = {"preprocess_fwd_kernel": wl5.N * 100 + R5 * 4, "bucket_scatter_kernel": wl5.N * 12 + R5 * 8,
+                       "tile_sort_kernel": R5 * 100, "tile_scan_kernel": T5 * 28}
+        extra["config5_novel_pose"]["stage_rooflines"] = {
+            k: {"algorithmic_bytes": b, "achieved_gbs": (b / (p5[k][1] / 5 * 1e-3) / 1e9) if k in p5 and p5[k][1] > 0 else None,
+                "frac_of_hbm": (b / (p5[k][1] / 5 * 1e-3) / 1e9 / peaks["hbm_gbs"]) if k in p5 and p5[k][1] > 0 else None}
+            for k, b in stage_bytes.items()}
+        del wl5, m5
+        torch.cuda.empty_cache()
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         torch.cuda.synchronize()
@@ -424,9 +522,9 @@ def main():
                                        f"L1/SSIM), {B} frames/GPU/step, global batch {B * world}", "poses": wl.pose_source,
                            "l2_policy": "inputs and activations (>1.5 GB/step) exceed the 126 MB L2; no explicit flush",
                            "parallelism": f"dp{world} (frames sharded, 1 all-reduce of 1.56M fp32 grads)",
-                           "step_graph": bool(trainer.use_graph and trainer._graphs)},
+                           "step_graph": step_graph_used},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "mlp_fwd_roofline": fwd_roofline, "raster_roofline": raster_roofline,
-                "cpu_baseline": cpu_baseline,
+                "cpu_baseline": cpu_baseline, **extra,
                 "kernel_ms_per_step": {k: round(v[1], 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1][1])},
                 "dominant_kernel": dominant}
         sys.stdout.flush()

@@ -61,6 +61,7 @@ class AvatarModel:
 
         if _assets is None:
             _assets, _frames, _pose_data, _transl_data = self._load_reference_assets(model_parms, train)
+        self._from_folder = not isinstance(_frames, list)
         S = int(model_parms.query_posmap_size)
         assert _assets["valid_idx"].numel() == S * S
         dev = self.device
@@ -82,7 +83,7 @@ class AvatarModel:
         self._rest_joints = _assets["rest_joints"].to(dev).float().contiguous()        # J(beta): constant per subject
         self.betas = _assets["betas"].to(dev).float()[None].expand(self.batch_size, -1) if "betas" in _assets else None
 
-        self.train_dataset = _FrameSet(_frames)
+        self.train_dataset = _FrameSet(_frames) if isinstance(_frames, list) else _frames
         num_training_frames = _pose_data.shape[0]
         self.pose = torch.nn.Embedding(num_training_frames, 72, _weight=_pose_data.clone().float(), sparse=True).to(dev)
         self.transl = torch.nn.Embedding(num_training_frames, 3, _weight=_transl_data.clone().float(), sparse=True).to(dev)
@@ -91,6 +92,8 @@ class AvatarModel:
         self.background = torch.tensor(bg_color, dtype=torch.float32, device=dev)
         self.optimizer = None
         self.scheduler = None
+        self.cache_decoder = not train     # inference models evaluate the frame-invariant stage-1 net once (see render_free_stage1)
+        self._dec_cache = None
         self.net_set(model_parms.train_stage)
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -105,16 +108,21 @@ class AvatarModel:
                    _pose_data=pose_data, _transl_data=transl_data, device=device)
 
     def _load_reference_assets(self, mp, train):
-        """Folder contract of the reference (model/avatar_model.py:41-98; scene/dataset_mono.py:83-160).  Needs the SMPL
-        model pickle for the rest joints; untested offline (the archive of README.md:41-54 is not available here)."""
+        """Folder contract of the reference (model/avatar_model.py:41-98; scene/dataset_mono.py:83-160): the training dataset (always
+        built, even for evaluation, avatar_model.py:41), the UV mask / canonical position map / LBS map / canonical joint
+        matrices, and the SMPL model pickle for the rest joints J(beta).  Exercised against a synthetic folder written in the
+        same layout (tests/test_dataset_cpu.py, tests/test_avatar_gpu.py)."""
+        from .dataset import MonoDataset_train
         split = "train" if train else "test"
+        dataset = MonoDataset_train(mp)
         S = int(mp.query_posmap_size)
         mask = np.load(join(mp.project_path, "assets", "uv_masks", f"uv_mask{S}_with_faceid_smpl.npy")).reshape(S, S)
         valid = torch.from_numpy(mask != -1).reshape(-1)
         qmap = torch.from_numpy(np.load(join(mp.source_path, split, f"query_posemap_{S}_cano_smpl.npz"))[f"posmap{S}"]).reshape(-1, 3)
         lbs = torch.from_numpy(np.load(join(mp.project_path, "assets", f"lbs_map_smpl_{S}.npy"))).reshape(S * S, 24)
-        cano = torch.load(join(mp.source_path, split, "smpl_cano_joint_mat.pth")).reshape(24, 4, 4)
-        smpl_data = torch.load(join(mp.source_path, "train", "smpl_parms.pth"))
+        cano = torch.load(join(mp.source_path, split, "smpl_cano_joint_mat.pth"), weights_only=False).reshape(24, 4, 4)
+        cano = torch.as_tensor(cano).float()
+        smpl_data = dataset.smpl_data
         beta = torch.as_tensor(smpl_data["beta"][0]).float()
         import pickle
         with open(join(mp.smpl_model_path, f"SMPL_{mp.smpl_gender.upper()}.pkl"), "rb") as f:
@@ -123,15 +131,16 @@ class AvatarModel:
         sd = torch.as_tensor(np.asarray(sm["shapedirs"])[:, :, :10]).double()
         Jr = torch.as_tensor(np.asarray(sm["J_regressor"].todense() if hasattr(sm["J_regressor"], "todense") else sm["J_regressor"])).double()
         rest = (Jr @ (v_t + torch.einsum("l,mkl->mk", beta.double(), sd))).float()
-        pose = torch.as_tensor(smpl_data["body_pose"]).float()
-        transl = torch.as_tensor(smpl_data["trans"]).float()
-        assets = dict(valid_idx=valid, query_points=qmap[valid], query_lbs=lbs[valid].float(), cano_joint_mats=cano, rest_joints=rest,
+        pose = dataset.pose_data.float()
+        transl = dataset.transl_data.float()
+        assets = dict(valid_idx=valid, query_points=qmap[valid].float(), query_lbs=lbs[valid].float(), cano_joint_mats=cano, rest_joints=rest,
                       betas=beta, S=S)
-        return assets, [], pose, transl
+        return assets, dataset, pose, transl
 
     # ------------------------------------------------------------------------------------------------------------------
     def net_set(self, mode):
         assert mode in [0, 1, 2]
+        self._dec_cache = None
         npm = self.net_parms
         self.net = POP_no_unet(c_geom=npm.c_geom, geom_layer_type=npm.geom_layer_type, nf=npm.nf, hsize=npm.hsize, up_mode=npm.up_mode,
                                use_dropout=bool(npm.use_dropout), uv_feat_dim=2).to(self.device)
@@ -153,6 +162,7 @@ class AvatarModel:
                     "scheduler": self.scheduler.state_dict()}, os.path.join(path, "net.pth"))
 
     def load(self, iteration, test=False):
+        self._dec_cache = None
         path = os.path.join(self.model_path, "net/iteration_{}".format(iteration))
         saved = torch.load(os.path.join(path, "net.pth"), weights_only=False)
         self.net.load_state_dict(saved["net"], strict=False)
@@ -189,6 +199,7 @@ class AvatarModel:
         return {"state": new_state, "param_groups": [g0, g1]}
 
     def stage_load(self, ckpt_path):
+        self._dec_cache = None
         saved = torch.load(os.path.join(ckpt_path, "net.pth"), weights_only=False)
         self.net.load_state_dict(saved["net"], strict=False)
         self.pose.load_state_dict(saved["pose"], strict=False)
@@ -196,7 +207,32 @@ class AvatarModel:
         self.geo_feature.data[...] = saved["geo_feature"].data[...]
 
     def getTrainDataloader(self):
-        return torch.utils.data.DataLoader(self.train_dataset, batch_size=self.batch_size, shuffle=True, num_workers=0, drop_last=True)
+        # model/avatar_model.py:238-244 (4 workers when the frames come from disk)
+        return torch.utils.data.DataLoader(self.train_dataset, batch_size=self.batch_size, shuffle=True,
+                                           num_workers=4 if self._from_folder else 0, drop_last=True)
+
+    def _need_folder(self, what):
+        if not self._from_folder:
+            raise RuntimeError(f"{what}: this AvatarModel was built from in-memory assets (from_assets); the dataset accessors read the "
+                               "reference's folder layout (scene/dataset_mono.py:83-96) given by model_parms.source_path / test_folder")
+
+    def getTestDataset(self):          # model/avatar_model.py:246-248
+        from .dataset import MonoDataset_test
+        self._need_folder("getTestDataset")
+        self.test_dataset = MonoDataset_test(self.model_parms)
+        return self.test_dataset
+
+    def getNovelposeDataset(self):     # model/avatar_model.py:250-252
+        from .dataset import MonoDataset_novel_pose
+        self._need_folder("getNovelposeDataset")
+        self.novel_pose_dataset = MonoDataset_novel_pose(self.model_parms)
+        return self.novel_pose_dataset
+
+    def getNovelviewDataset(self):     # model/avatar_model.py:254-256
+        from .dataset import MonoDataset_novel_view
+        self._need_folder("getNovelviewDataset")
+        self.novel_view_dataset = MonoDataset_novel_view(self.model_parms)
+        return self.novel_view_dataset
 
     def zero_grad(self, epoch):
         self.optimizer.zero_grad()
@@ -286,7 +322,8 @@ class AvatarModel:
         plan = self.raster_plan(B, P, H, W)
         self._last_plan = plan
         images = rasterize_batch(means, colors, scales, self.fix_rotation, self.fix_opacity, cams, self.background, plan)
-        if not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing() and not plan.check(wait=True):   # inference: make the result right before returning it
+        if (not torch.is_grad_enabled() and not torch.cuda.is_current_stream_capturing() and not getattr(self, "defer_raster_check", False)
+                and not plan.check(wait=True)):          # inference: make the result right before returning it (unless the caller checks later)
             images = rasterize_batch(means, colors, scales, self.fix_rotation, self.fix_opacity, cams, self.background, plan)
             if not plan.check(wait=True):
                 raise RuntimeError("batched rasterizer: binning buffer overflowed twice in a row")
@@ -346,17 +383,34 @@ class AvatarModel:
         raise NotImplementedError("train_stage 2 (pose-encoder U-Net) is the next scope row (SURVEY.md §8f rank 2)")
 
     def render_free_stage1(self, batch_data, iteration):
-        """model/avatar_model.py:467-554: same forward minus the losses (BatchNorm still uses batch statistics)."""
+        """model/avatar_model.py:467-554: same forward minus the losses (BatchNorm still uses batch statistics).
+
+        In stage 1 the feature net's inputs (geo_feature, the uv grid) do not depend on the frame, so its output is the same for every
+        frame the reference renders: a model built for inference (`train=False`, what eval.py /
+        render_novel_pose.py construct) evaluates the net ONCE and reuses the packed output until parameters are loaded again
+        (`cache_decoder`).  Per frame that leaves SMPL -> LBS -> rasterizer.  Only the BatchNorm running statistics (never used for
+        normalisation by the reference's scripts) stop being updated by the skipped evaluations."""
+        S = int(self.model_parms.query_posmap_size)
         if "pose_data" in batch_data:      # novel-pose datasets carry the pose instead of an embedding index
-            pose_batch, transl_batch = batch_data["pose_data"], batch_data["transl_data"]
-            cano2live = SmplCano2Live.apply(pose_batch, transl_batch, self._rest_joints, self._inv_cano)
-            S = int(self.model_parms.query_posmap_size)
-            dec = self.net.forward_packed(self.geo_feature, S, pose_batch.shape[0])
-            scale_mul = 1e-3 * iteration if iteration < 1000 else 1.0
-            means, scales, colors = LbsAssemble.apply(dec, cano2live, self.valid_index, self._query_points, self._query_lbs, scale_mul)
+            pose_batch, transl_batch = batch_data["pose_data"].float(), batch_data["transl_data"].float()
         else:
-            means, scales, colors, _ = self._posed_gaussians(batch_data["pose_idx"], iteration)
+            idx = batch_data["pose_idx"]
+            pose_batch, transl_batch = self.pose(idx), self.transl(idx)
+        B = pose_batch.shape[0]
+        cano2live = SmplCano2Live.apply(pose_batch, transl_batch, self._rest_joints, self._inv_cano)
+        cached = getattr(self, "_dec_cache", None)
+        if self.cache_decoder and not torch.is_grad_enabled() and cached is not None:
+            dec = cached
+        else:
+            dec = self.net.forward_packed(self.geo_feature, S, B)
+            if self.cache_decoder and not torch.is_grad_enabled():
+                self._dec_cache = dec.detach()
+        scale_mul = 1e-3 * iteration if iteration < 1000 else 1.0
+        means, scales, colors = LbsAssemble.apply(dec, cano2live, self.valid_index, self._query_points, self._query_lbs, scale_mul)
         return self._render_frames(batch_data, means, scales, colors)
+
+    def invalidate_decoder_cache(self):
+        self._dec_cache = None
 
     def render_free_stage2(self, batch_data, iteration):
         raise NotImplementedError("train_stage 2 (pose-encoder U-Net) is the next scope row (SURVEY.md §8f rank 2)")

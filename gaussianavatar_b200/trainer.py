@@ -42,8 +42,12 @@ class _StepGraph:
 
 
 class Stage1Trainer:
-    def __init__(self, model, fused_adam: bool = True, process_group=None, use_graph=None):
+    def __init__(self, model, fused_adam: bool = True, process_group=None, use_graph=None, perceptual_loss=None):
         self.model = model
+        # train.py:26,89-91: after `lpips_start_iter` epochs the reference adds lambda_lpips * LPIPS((image-0.5)*2, (gt-0.5)*2).  LPIPS is
+        # an external pretrained network (out of scope): pass any callable(image, gt) -> scalar here to get the term
+        self.perceptual_loss = perceptual_loss
+        self._warned_lpips = False
         # whole-step CUDA graph (forward + loss + backward in ONE launch; all-reduce and Adam follow eagerly): on unless GA_STEP_GRAPH=0
         self.use_graph = (os.environ.get("GA_STEP_GRAPH", "1") != "0") if use_graph is None else bool(use_graph)
         self._graphs = {}
@@ -51,12 +55,20 @@ class Stage1Trainer:
         self.opt = model.opt_parms
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.group = process_group
-        model.training_setup()
-        if fused_adam:
+        # the caller may already have followed the reference's resume order (training_setup() -> load(), train.py:36-45): keep what it loaded
+        prev_opt = model.optimizer.state_dict() if model.optimizer is not None else None
+        prev_sched = model.scheduler.state_dict() if model.scheduler is not None else None
+        if model.optimizer is None:
+            model.training_setup()
+        if fused_adam and not isinstance(model.optimizer, FusedAdam):
             # same hyper-parameters / groups / state layout as the torch.optim.Adam the reference builds (avatar_model.py:150-155)
             model.optimizer = FusedAdam([{"params": list(model.net.parameters()), "lr": self.opt.lr_net},
                                          {"params": [model.geo_feature], "lr": self.opt.lr_geomfeat}])
             model.scheduler = torch.optim.lr_scheduler.MultiStepLR(model.optimizer, self.opt.sched_milestones, gamma=0.1)
+            if prev_opt is not None and prev_opt.get("state"):
+                model.optimizer.load_state_dict(model.translate_optimizer_state(prev_opt))
+            if prev_sched is not None and prev_sched.get("last_epoch", 0) > 0:
+                model.scheduler.load_state_dict(prev_sched)
         self._comm_stream = None
 
     def loss(self, batch, iteration: int, epoch: int = 0):
@@ -65,6 +77,15 @@ class Stage1Trainer:
         image, points, offset_loss, geo_loss, scale_loss = m.train_stage1(batch, iteration)
         wdecay_rgl = adjust_loss_weights(o.lambda_rgl, epoch, mode="decay", start=self.epoch_start, every=20)   # train.py:60
         loss = o.lambda_scale * scale_loss + wdecay_rgl * offset_loss + image_loss(image, batch["original_image"], o.lambda_dssim) + geo_loss
+        if epoch > o.lpips_start_iter:                   # train.py:89-91
+            if self.perceptual_loss is not None:
+                gt = batch["original_image"]
+                loss = loss + o.lambda_lpips * torch.mean(self.perceptual_loss((image - 0.5) * 2, (gt - 0.5) * 2))
+            elif not self._warned_lpips:
+                import warnings
+                warnings.warn(f"epoch {epoch} > lpips_start_iter {o.lpips_start_iter}: the reference adds lambda_lpips * LPIPS from here on "
+                              "(train.py:89-91) but no perceptual_loss callable was given to Stage1Trainer; the term is omitted")
+                self._warned_lpips = True
         return loss, image
 
     epoch_start = 0    # train.py:38-45: 0 unless resuming from a checkpoint
@@ -144,6 +165,33 @@ class Stage1Trainer:
             g["lr"] = lr
 
     # ---- whole-step CUDA graph -------------------------------------------------------------------------------------------------
+    def sync_pose_gradients(self, epoch):
+        """Pose optimisation under data parallelism (epoch > pose_op_start_iter): every rank must apply the SAME sparse update to its
+        replica of the pose / transl tables.  The touched rows (this rank's frames) and their gradients are all-gathered, scaled by
+        1/world (the global loss is the mean of the ranks' losses) and installed as the sparse gradient SparseAdam steps on."""
+        m = self.model
+        if self.world == 1 or epoch <= self.opt.pose_op_start_iter:
+            return
+        for emb in (m.pose, m.transl):
+            g = emb.weight.grad
+            if g is None:
+                continue
+            g = g.coalesce()
+            idx, val = g.indices()[0].contiguous(), g.values().contiguous()
+            n = torch.tensor([idx.numel()], device=idx.device)
+            counts = [torch.zeros_like(n) for _ in range(self.world)]
+            dist.all_gather(counts, n, group=self.group)
+            nmax = int(max(int(c) for c in counts))
+            pad_i = torch.zeros(nmax, dtype=idx.dtype, device=idx.device); pad_i[:idx.numel()] = idx
+            pad_v = torch.zeros(nmax, val.shape[1], dtype=val.dtype, device=val.device); pad_v[:idx.numel()] = val
+            all_i = [torch.zeros_like(pad_i) for _ in range(self.world)]
+            all_v = [torch.zeros_like(pad_v) for _ in range(self.world)]
+            dist.all_gather(all_i, pad_i, group=self.group)
+            dist.all_gather(all_v, pad_v, group=self.group)
+            ii = torch.cat([a[:int(c)] for a, c in zip(all_i, counts)])
+            vv = torch.cat([a[:int(c)] for a, c in zip(all_v, counts)]) / self.world
+            emb.weight.grad = torch.sparse_coo_tensor(ii[None], vv, emb.weight.shape).coalesce()
+
     def _graph_applicable(self, batch, iteration, epoch) -> bool:
         """The captured step holds no host-dependent value: the scale ramp is over (iteration >= 1000, avatar_model.py:316-319), pose
         optimisation is inactive (its sparse embedding gradients are then never read, avatar_model.py:261-270) and the frames share
@@ -151,6 +199,7 @@ class Stage1Trainer:
         m = self.model
         img = batch.get("original_image")
         return (self.use_graph and isinstance(m.optimizer, FusedAdam) and iteration >= 1000 and epoch <= self.opt.pose_op_start_iter
+                and not (self.perceptual_loss is not None and epoch > self.opt.lpips_start_iter)
                 and torch.is_tensor(img) and img.is_cuda and img.shape[0] <= 8 and os.environ.get("GA_RASTER_BATCHED", "1") != "0"
                 and m._uniform_frames(batch, img.shape[0]))
 
@@ -233,6 +282,7 @@ class Stage1Trainer:
             m.zero_grad(epoch)
             loss.backward()
         self.sync_gradients()
+        self.sync_pose_gradients(epoch)
         if isinstance(m.optimizer, FusedAdam):
             m.optimizer.grad_scale = 1.0 / self.world
             plan = getattr(m, "_last_plan", None)

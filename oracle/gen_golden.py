@@ -37,6 +37,35 @@ def gen_test_pose_subset():
                         trans=s["trans"].numpy()[idx], frame_index=idx, intrinsic=c["intrinsic"], extrinsic=c["extrinsic"])
 
 
+def gen_dataset_items():
+    """Items of the reference's own dataset classes (scene/dataset_mono.py) on the synthetic folder tests/dataset_fixture.py writes."""
+    import tempfile
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from dataset_fixture import write_synthetic_dataset
+    from scene import dataset_mono as ref
+    _orig = ref.getProjectionMatrix      # numpy-1.x semantics of the reference env (python float / np.float32 -> float64 scalar): see gen_camera
+    ref.getProjectionMatrix = lambda **kw: _orig(**{**kw, "K": np.asarray(kw["K"]).astype(np.float64)})
+    fields = ("original_image", "world_view_transform", "projection_matrix", "full_proj_transform", "camera_center")
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        mp = write_synthetic_dataset(tmp, stage2=True)
+        mp.no_mask = 1      # the reference's masked branch (dataset_mono.py:214) feeds an int8 array to PIL, which the Pillow of this image rejects
+        sets = dict(train=ref.MonoDataset_train(mp, device="cpu"), test=ref.MonoDataset_test(mp, device="cpu"),
+                    novel_pose=ref.MonoDataset_novel_pose(mp, device="cpu"))
+        for name, dset in sets.items():
+            out[f"{name}/len"] = np.array(len(dset))
+            for i in (0, len(dset) - 1):
+                item = dset[i]
+                for k in fields:
+                    if k in item:
+                        out[f"{name}/{i}/{k}"] = np.asarray(item[k], dtype=np.float32)
+                out[f"{name}/{i}/scalars"] = np.array([item["FovX"], item["FovY"], item["width"], item["height"], item["pose_idx"]], dtype=np.float64)
+                for k in ("pose_data", "transl_data", "inp_pos_map"):
+                    if k in item:
+                        out[f"{name}/{i}/{k}"] = np.asarray(item[k], dtype=np.float32)
+    np.savez_compressed(os.path.join(OUT, "dataset_items.npz"), **out)
+
+
 def gen_smpl_A():
     body = syn.make_body(0)
     d = np.load(os.path.join(OUT, "test_pose_subset.npz"))
@@ -160,5 +189,6 @@ if __name__ == "__main__":
     gen_camera()
     gen_param_order()
     gen_unet()
+    gen_dataset_items()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -188,3 +188,71 @@ def test_train_stage1_end_to_end_vs_oracle_chain():
     assert model.net.flat.grad is not None and torch.isfinite(model.net.flat.grad).all() and model.net.flat.grad.abs().sum() > 0
     assert model.geo_feature.grad is not None and torch.isfinite(model.geo_feature.grad).all()
     assert model.pose.weight.grad is not None
+
+
+def test_reference_signature_constructor_reads_the_dataset_folder(tmp_path):
+    """AvatarModel(model_parms, net_parms, opt_parms) (model/avatar_model.py:20-121) on a synthetic folder in the reference's layout:
+    the staged tensors equal the in-memory construction from the same assets, the DataLoader yields reference-shaped batches and a
+    stage-1 step, the test / novel-pose datasets render."""
+    from dataset_fixture import write_synthetic_dataset
+    from gaussianavatar_b200 import synthetic as syn
+    from gaussianavatar_b200.avatar_model import AvatarModel
+    from gaussianavatar_b200.config import NetworkParams, OptimizationParams
+    from gaussianavatar_b200.losses import image_loss
+    from gaussianavatar_b200.workload import to_cuda
+    N, S, F = 600, 32, 5
+    mp = write_synthetic_dataset(str(tmp_path), N=N, S=S, num_frames=F, side=64, inp=16)
+    torch.manual_seed(0)
+    m = AvatarModel(mp, NetworkParams(), OptimizationParams(), train=True)
+    a = syn.make_avatar_assets(N, S, seed=0)
+    pose, transl = syn.synthetic_poses(F, seed=0)
+    ref = AvatarModel.from_assets(a, [], pose, transl, batch_size=2)
+    assert torch.equal(m.valid_idx, ref.valid_idx) and torch.equal(m.valid_index, ref.valid_index)
+    for name in ("_query_points", "_query_lbs", "_inv_cano"):
+        assert torch.allclose(getattr(m, name), getattr(ref, name), atol=1e-6), name
+    assert torch.allclose(m._rest_joints, ref._rest_joints, atol=1e-5)
+    assert torch.equal(m.pose.weight, ref.pose.weight) and torch.equal(m.transl.weight, ref.transl.weight)
+    assert m.geo_feature.shape == (1, 64, 16, 16)
+
+    m.training_setup()
+    batch = next(iter(m.getTrainDataloader()))
+    assert batch["original_image"].shape == (2, 3, 64, 64) and batch["world_view_transform"].shape == (2, 4, 4)
+    batch, _ = to_cuda(batch, DEV)
+    image, points, offset_loss, geo_loss, scale_loss = m.train_stage1(batch, 2000)
+    loss = image_loss(image, batch["original_image"].float(), 0.2) + 10.0 * offset_loss + geo_loss + 3e-2 * scale_loss
+    m.zero_grad(1); loss.backward(); m.step(1)
+    assert torch.isfinite(loss) and image.shape == (2, 3, 64, 64) and (image < 0.999).any()
+
+    te = m.getTestDataset()
+    item = te[0]
+    tb, _ = to_cuda({k: (v[None] if torch.is_tensor(v) else [v]) for k, v in item.items()}, DEV)
+    tb["pose_idx"] = torch.tensor([item["pose_idx"]], device=DEV)
+    with torch.no_grad():
+        img = m.render_free_stage1(tb, 59400)
+    assert img.shape == (1, 3, 64, 64)
+    nv = m.getNovelposeDataset()
+    assert len(nv) == 4 and nv[0]["height"] == 1024
+
+
+def test_inference_model_caches_the_frame_invariant_decoder_output():
+    """render_novel_pose.py path (avatar_model.py:467-554): an inference model evaluates the stage-1 net once; the frames rendered from
+    the cached output are the frames a model that re-evaluates it every time renders."""
+    from gaussianavatar_b200 import synthetic as syn
+    from gaussianavatar_b200.avatar_model import AvatarModel
+    from gaussianavatar_b200.workload import Stage1Workload
+    wl = Stage1Workload(3, 1, device=DEV, N=4000, S=64, side=128, inp_posmap_size=32)
+    m = wl.model
+    pose, transl = syn.synthetic_poses(3, seed=4)
+    batches = [dict(pose_idx=torch.tensor([0], device=DEV), pose_data=pose[i:i + 1].to(DEV), transl_data=transl[i:i + 1].to(DEV),
+                    **wl.camera_fields(1)) for i in range(3)]
+    with torch.no_grad():
+        m.cache_decoder = False
+        ref = [m.render_free_stage1(b, 59400).clone() for b in batches]
+        m.cache_decoder = True
+        m.invalidate_decoder_cache()
+        n0 = list(m.net._states.values())[0].num_batches_tracked
+        got = [m.render_free_stage1(b, 59400).clone() for b in batches]
+        assert list(m.net._states.values())[0].num_batches_tracked == n0 + 1          # evaluated once for the three frames
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    assert not torch.equal(got[0], got[1])

@@ -54,3 +54,50 @@ def test_frame_sharding_is_disjoint_and_covers_the_global_batch():
             assert len(set(seen)) == len(seen) == world * W.B
             base = step * world * W.B
             assert sorted(seen) == sorted((base + j) % W.num_frames for j in range(world * W.B))
+
+
+def _pose_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from types import SimpleNamespace
+    from gaussianavatar_b200.trainer import Stage1Trainer
+    torch.manual_seed(0)
+    pose = torch.nn.Embedding(10, 72, sparse=True); transl = torch.nn.Embedding(10, 3, sparse=True)      # identical replicas
+    ids = torch.tensor([2 * rank, 2 * rank + 1])                                                        # this rank's frames
+    w = torch.arange(72.0) * (rank + 1)
+    ((pose(ids) * w).sum() + (transl(ids) * (rank + 2.0)).sum()).backward()
+    tr = Stage1Trainer.__new__(Stage1Trainer)
+    tr.model = SimpleNamespace(pose=pose, transl=transl)
+    tr.world, tr.group, tr.opt = world, None, SimpleNamespace(pose_op_start_iter=5)
+    tr.sync_pose_gradients(epoch=3)                       # inactive: untouched
+    assert pose.weight.grad.coalesce().indices().shape[1] == 2
+    tr.sync_pose_gradients(epoch=9)
+    g = pose.weight.grad.to_dense()
+    expect = torch.zeros(10, 72)
+    for r in range(world):
+        expect[2 * r] = expect[2 * r + 1] = torch.arange(72.0) * (r + 1) / world
+    ok = torch.allclose(g, expect) and torch.allclose(transl.weight.grad.to_dense()[:4, 0], torch.tensor([1.0, 1.0, 1.5, 1.5]))
+    # SparseAdam on the synchronised gradient keeps the replicas identical
+    opt = torch.optim.SparseAdam(list(pose.parameters()) + list(transl.parameters()), 5e-3)
+    opt.step()
+    gathered = [torch.zeros_like(pose.weight.data) for _ in range(world)]
+    dist.all_gather(gathered, pose.weight.data)
+    ok = ok and torch.equal(gathered[0], gathered[1])
+    if rank == 0:
+        out.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pose_embedding_gradients_are_synchronised_across_ranks_gloo():
+    """with pose optimisation active, ranks must apply the same sparse update to their replicas of the pose tables."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_pose_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
