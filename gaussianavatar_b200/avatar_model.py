@@ -56,8 +56,8 @@ class AvatarModel:
         assert model_parms.smpl_type in ["smplx", "smpl"]
         if model_parms.smpl_type != "smpl":
             raise NotImplementedError("only smpl_type='smpl' (24 joints, the reference default) is built")
-        if model_parms.train_stage not in (0, 1):
-            raise NotImplementedError("train_stage 2 (pose-encoder U-Net) is the next scope row (SURVEY.md §8f rank 2)")
+        if model_parms.train_stage not in (0, 1, 2):
+            raise ValueError(f"train_stage {model_parms.train_stage} is not one of 1, 2")
 
         if _assets is None:
             _assets, _frames, _pose_data, _transl_data = self._load_reference_assets(model_parms, train)
@@ -147,16 +147,30 @@ class AvatarModel:
         inp = self.model_parms.inp_posmap_size
         geo = torch.ones(1, npm.c_geom, inp, inp).normal_(mean=0., std=0.01).float().to(self.device)      # avatar_model.py:136
         self.geo_feature = nn.Parameter(geo.requires_grad_(True))
+        if self.model_parms.train_stage == 2:                                                              # avatar_model.py:138-146
+            from .pose_encoder import UnetNoCond5DS
+            if npm.c_pose != npm.c_geom:
+                raise NotImplementedError("c_pose must equal c_geom: the two maps are ADDED (model/network.py:58)")
+            self.pose_encoder = UnetNoCond5DS(input_nc=3, output_nc=npm.c_pose, nf=npm.nf, up_mode=npm.up_mode, use_dropout=False).to(self.device)
 
     def training_setup(self):
-        # avatar_model.py:148-162 (stage 1)
-        self.optimizer = torch.optim.Adam([{"params": self.net.parameters(), "lr": self.opt_parms.lr_net},
-                                           {"params": self.geo_feature, "lr": self.opt_parms.lr_geomfeat}])
+        # avatar_model.py:148-162: stage 1 trains the net and geo_feature; stage 2 the net at a tenth of the rate and the pose encoder
+        if self.model_parms.train_stage == 2:
+            self.optimizer = torch.optim.Adam([{"params": self.net.parameters(), "lr": self.opt_parms.lr_net * 0.1},
+                                               {"params": self.pose_encoder.parameters(), "lr": self.opt_parms.lr_net}])
+        else:
+            self.optimizer = torch.optim.Adam([{"params": self.net.parameters(), "lr": self.opt_parms.lr_net},
+                                               {"params": self.geo_feature, "lr": self.opt_parms.lr_geomfeat}])
         self.scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optimizer, self.opt_parms.sched_milestones, gamma=0.1)
 
     def save(self, iteration):
         path = os.path.join(self.model_path, "net/iteration_{}".format(iteration))
         os.makedirs(path, exist_ok=True)
+        if self.model_parms.train_stage == 2:                      # avatar_model.py:177-186
+            torch.save({"pose_encoder": self.pose_encoder.state_dict(), "geo_feature": self.geo_feature, "pose": self.pose.state_dict(),
+                        "transl": self.transl.state_dict(), "net": self.net.state_dict(), "optimizer": self.optimizer.state_dict(),
+                        "scheduler": self.scheduler.state_dict()}, os.path.join(path, "pose_encoder.pth"))
+            return
         torch.save({"net": self.net.state_dict(), "geo_feature": self.geo_feature, "pose": self.pose.state_dict(),
                     "transl": self.transl.state_dict(), "optimizer": self.optimizer.state_dict(),
                     "scheduler": self.scheduler.state_dict()}, os.path.join(path, "net.pth"))
@@ -166,10 +180,11 @@ class AvatarModel:
         path = os.path.join(self.model_path, "net/iteration_{}".format(iteration))
         saved = torch.load(os.path.join(path, "net.pth"), weights_only=False)
         self.net.load_state_dict(saved["net"], strict=False)
-        if not test:
-            self.pose.load_state_dict(saved["pose"], strict=False)
-            self.transl.load_state_dict(saved["transl"], strict=False)
-        self.geo_feature.data[...] = saved["geo_feature"].data[...]
+        if self.model_parms.train_stage == 1:                      # avatar_model.py:197-202
+            if not test:
+                self.pose.load_state_dict(saved["pose"], strict=False)
+                self.transl.load_state_dict(saved["transl"], strict=False)
+            self.geo_feature.data[...] = saved["geo_feature"].data[...]
         # optimizer state: written either by this implementation (ONE flat net parameter + geo_feature) or by the reference
         # (53 per-tensor Adam states + geo_feature, avatar_model.py:148-155): the latter is re-laid out into the flat buffer
         if self.optimizer is not None and "optimizer" in saved:
@@ -206,6 +221,18 @@ class AvatarModel:
         self.transl.load_state_dict(saved["transl"], strict=False)
         self.geo_feature.data[...] = saved["geo_feature"].data[...]
 
+    def stage2_load(self, epoch):
+        """avatar_model.py:223-236: everything a stage-2 run saved (`pose_encoder.pth`)."""
+        self._dec_cache = None
+        path = os.path.join(self.model_parms.project_path, self.model_path, "net/iteration_{}".format(epoch))
+        saved = torch.load(os.path.join(path, "pose_encoder.pth"), weights_only=False)
+        self.net.load_state_dict(saved["net"], strict=False)
+        self.pose.load_state_dict(saved["pose"], strict=False)
+        self.transl.load_state_dict(saved["transl"], strict=False)
+        self.geo_feature.data[...] = saved["geo_feature"].data[...]
+        self.pose_encoder.load_state_dict(saved["pose_encoder"], strict=False)
+        return getattr(self, "novel_view_dataset", None)
+
     def getTrainDataloader(self):
         # model/avatar_model.py:238-244 (4 workers when the frames come from disk)
         return torch.utils.data.DataLoader(self.train_dataset, batch_size=self.batch_size, shuffle=True,
@@ -236,13 +263,13 @@ class AvatarModel:
 
     def zero_grad(self, epoch):
         self.optimizer.zero_grad()
-        if epoch > self.opt_parms.pose_op_start_iter:
+        if self.model_parms.train_stage == 1 and epoch > self.opt_parms.pose_op_start_iter:     # avatar_model.py:258-262
             self.optimizer_pose.zero_grad()
 
     def step(self, epoch):
         self.optimizer.step()
         self.scheduler.step()
-        if epoch > self.opt_parms.pose_op_start_iter:
+        if self.model_parms.train_stage == 1 and epoch > self.opt_parms.pose_op_start_iter:     # avatar_model.py:263-270
             self.optimizer_pose.step()
 
     # ------------------------------------------------------------------------------------------------------------------
@@ -379,8 +406,27 @@ class AvatarModel:
         images = self._render_frames(batch_data, means, scales, colors)
         return images, means, offset_loss, geo_loss, scale_loss
 
+    def _stage2_gaussians(self, batch_data):
+        """Stage 2 (model/avatar_model.py:369-420 / :557-612): the pose encoder turns each frame's posed-body position map into a
+        feature map that is ADDED to the geometry features, so the decoder runs per frame (B*S*S rows, BatchNorm statistics over all of
+        them); no scale ramp in this stage."""
+        inp = batch_data["inp_pos_map"].to(self.device).float()
+        idx = batch_data["pose_idx"]
+        cano2live = SmplCano2Live.apply(self.pose(idx), self.transl(idx), self._rest_joints, self._inv_cano)
+        S = int(self.model_parms.query_posmap_size)
+        pose_featmap = self.pose_encoder(inp)                                                         # [B,64,h,h]
+        dec = self.net.forward_packed_frames(self.geo_feature, pose_featmap, S)                      # [B*S*S, 8]
+        means, scales, colors = LbsAssemble.apply(dec, cano2live, self.valid_index, self._query_points, self._query_lbs, 1.0, True)
+        return means, scales, colors, dec, pose_featmap
+
     def train_stage2(self, batch_data, iteration):
-        raise NotImplementedError("train_stage 2 (pose-encoder U-Net) is the next scope row (SURVEY.md §8f rank 2)")
+        """model/avatar_model.py:369-463: returns (images [B,3,H,W], full_pred [B,N,3], pose_loss, offset_loss)."""
+        means, scales, colors, dec, pose_featmap = self._stage2_gaussians(batch_data)
+        offset_loss = torch.mean((dec[:, :3] * 0.02) ** 2)          # mean over B x S*S x 3 (avatar_model.py:424)
+        pose_loss = torch.mean(pose_featmap ** 2)
+        self._last_gaussians = (means, scales, colors)
+        images = self._render_frames(batch_data, means, scales, colors)
+        return images, means, pose_loss, offset_loss
 
     def render_free_stage1(self, batch_data, iteration):
         """model/avatar_model.py:467-554: same forward minus the losses (BatchNorm still uses batch statistics).
@@ -413,4 +459,6 @@ class AvatarModel:
         self._dec_cache = None
 
     def render_free_stage2(self, batch_data, iteration):
-        raise NotImplementedError("train_stage 2 (pose-encoder U-Net) is the next scope row (SURVEY.md §8f rank 2)")
+        """model/avatar_model.py:557-649: the stage-2 forward without the losses."""
+        means, scales, colors, _, _ = self._stage2_gaussians(batch_data)
+        return self._render_frames(batch_data, means, scales, colors)

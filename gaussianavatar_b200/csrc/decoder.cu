@@ -72,6 +72,7 @@ struct Workspace {
     float *F[4];          // NHWC [Hf*Wf, 64]: geo, conv1, conv2, conv3 (tensor-core path: F[0..2] hold TF32-rounded values)
     float *wr;            // [3][25*64*64] TF32-rounded copy of the conv weights (tensor-core path)
     float *dF[2];         // ping-pong gradients of the above
+    float *Fp, *dFp;      // [frames][Hf*Wf, 64]: per-frame input map conv3(geo) + pose_featmap (stage 2, model/network.py:58) and its gradient
     float *feat;          // [M, 72]
     float *d_feat;        // [M, 72]
     float *Y[5];          // [M,128] pre-BN outputs of layers 1..5
@@ -83,14 +84,16 @@ struct Workspace {
     size_t total;
 };
 
-Workspace carve_ws(void *buf, int S, int Hf)
+Workspace carve_ws(void *buf, int S, int Hf, int frames)
 {
     Carver c(buf);
     Workspace w;
-    const size_t M = (size_t)S * S, P = (size_t)Hf * Hf;
+    const size_t M = (size_t)frames * S * S, P = (size_t)Hf * Hf;
     for (int i = 0; i < 4; ++i) w.F[i] = c.take<float>(P * kCg);
     for (int i = 0; i < 2; ++i) w.dF[i] = c.take<float>(P * kCg);
     w.wr = c.take<float>((size_t)3 * 25 * kCg * kCg);
+    w.Fp = c.take<float>(frames > 1 ? (size_t)frames * P * kCg : 4);
+    w.dFp = c.take<float>(frames > 1 ? (size_t)frames * P * kCg : 4);
     w.feat = c.take<float>(M * kFeatLd);
     w.d_feat = c.take<float>(M * kFeatLd);
     for (int i = 0; i < 5; ++i) w.Y[i] = c.take<float>(M * kH);
@@ -138,6 +141,32 @@ __global__ void __launch_bounds__(256) hwc_to_chw_kernel(const float *__restrict
     }
 }
 
+// out[p][c] = in_chw[c][p] + base[p][c]: the per-frame decoder input map of stage 2, pose_featmap + geom_featmap (model/network.py:58)
+__global__ void __launch_bounds__(256) chw_to_hwc_add_kernel(const float *__restrict__ in, const float *__restrict__ base, float *__restrict__ out, int P)
+{
+    __shared__ float t[64][65];
+    const int p0 = blockIdx.x * 64;
+    in += (size_t)blockIdx.y * 64 * P; out += (size_t)blockIdx.y * 64 * P;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int c = i / 64, p = i % 64;
+        t[c][p] = (p0 + p < P) ? in[(size_t)c * P + p0 + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int p = i / 64, c = i % 64;
+        if (p0 + p < P) out[(size_t)(p0 + p) * 64 + c] = t[c][p] + base[(size_t)(p0 + p) * 64 + c];
+    }
+}
+// out[i] = sum_f in[f][i]
+__global__ void __launch_bounds__(256) sum_frames_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, size_t n4, int frames)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = in[i];
+    for (int f = 1; f < frames; ++f) { const float4 v = in[(size_t)f * n4 + i]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    out[i] = a;
+}
+
 // Bilinear taps of F.grid_sample(align_corners=False, zeros) for query pixel (row i, col j) of an S x S UV grid over an
 // Hf x Hf map — same fp32 operation order as torch: u = idx/(S-1); g = u*2-1; ix = ((g+1)*size-1)/2.
 struct Taps {
@@ -158,16 +187,18 @@ __device__ __forceinline__ Taps make_taps(int i, int j, int S, int Hf)
 
 // feat[m, 0:64] = bilinear(F3), feat[m,64] = row/(S-1), feat[m,65] = col/(S-1), feat[m,66:72] = 0.  16 threads / pixel.
 __global__ void __launch_bounds__(256)
-sample_feat_fwd_kernel(int S, int Hf, const float *__restrict__ F, float *__restrict__ feat)
+sample_feat_fwd_kernel(int S, int Hf, int frames, size_t frame_stride, const float *__restrict__ F, float *__restrict__ feat)
 {
     const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
     const size_t m = gid >> 4;
     const int q = (int)(gid & 15);
-    if (m >= (size_t)S * S) return;
-    const int i = (int)(m / S), j = (int)(m % S);
+    if (m >= (size_t)frames * S * S) return;
+    const size_t ml = m % ((size_t)S * S);             // pixel inside its frame; the frame's map starts frame_stride floats further
+    F += (m / ((size_t)S * S)) * frame_stride;
+    const int i = (int)(ml / S), j = (int)(ml % S);
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (Hf == S) {
-        o = *reinterpret_cast<const float4 *>(F + m * kCg + q * 4);
+        o = *reinterpret_cast<const float4 *>(F + ml * kCg + q * 4);
     } else {
         const Taps t = make_taps(i, j, S, Hf);
 #pragma unroll
@@ -191,16 +222,18 @@ sample_feat_fwd_kernel(int S, int Hf, const float *__restrict__ F, float *__rest
 
 // transpose of the above: scatter d_feat[m, 0:64] into dF (pre-zeroed) with 16-byte vector reductions
 __global__ void __launch_bounds__(256)
-sample_feat_bwd_kernel(int S, int Hf, const float *__restrict__ d_feat, float *__restrict__ dF)
+sample_feat_bwd_kernel(int S, int Hf, int frames, size_t frame_stride, const float *__restrict__ d_feat, float *__restrict__ dF)
 {
     const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
     const size_t m = gid >> 4;
     const int q = (int)(gid & 15);
-    if (m >= (size_t)S * S) return;
-    const int i = (int)(m / S), j = (int)(m % S);
+    if (m >= (size_t)frames * S * S) return;
+    const size_t ml = m % ((size_t)S * S);
+    dF += (m / ((size_t)S * S)) * frame_stride;
+    const int i = (int)(ml / S), j = (int)(ml % S);
     const float4 g = *reinterpret_cast<const float4 *>(d_feat + m * kFeatLd + q * 4);
     if (Hf == S) {
-        red_add_v4(dF + m * kCg + q * 4, g.x, g.y, g.z, g.w);
+        red_add_v4(dF + ml * kCg + q * 4, g.x, g.y, g.z, g.w);
         return;
     }
     const Taps t = make_taps(i, j, S, Hf);
@@ -526,6 +559,7 @@ int check_desc(const GaDecoderDesc *d)
     GA_REQUIRE(d->c_geom == kCg && d->hsize == kH, "only c_geom=64, hsize=128 (the reference defaults, arguments/__init__.py:101-111) are built");
     GA_REQUIRE(d->S >= 2 && d->feat_res >= 1 && d->batch >= 1, "bad decoder dims S=%d feat_res=%d batch=%d", d->S, d->feat_res, d->batch);
     GA_REQUIRE((d->S * (long long)d->S) % 4 == 0, "S*S must be a multiple of 4");
+    GA_REQUIRE(d->frames >= 0 && d->frames <= 8 && (long long)(d->frames ? d->frames : 1) * d->S * d->S < (1ll << 30), "bad decoder frames=%d", d->frames);
     return GA_OK;
 }
 
@@ -550,20 +584,22 @@ extern "C" int ga_decoder_layout(const GaDecoderDesc *d, GaDecoderLayout *out)
 extern "C" size_t ga_decoder_workspace_bytes(const GaDecoderDesc *d)
 {
     if (check_desc(d)) return 0;
-    return carve_ws(nullptr, d->S, d->feat_res).total;
+    return carve_ws(nullptr, d->S, d->feat_res, d->frames ? d->frames : 1).total;
 }
 
-extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, const float *geo_nchw, float *bn_running,
-                                  void *workspace, float *dec_out, void *stream_)
+extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, const float *geo_nchw, const float *pose_feat_nchw,
+                                  float *bn_running, void *workspace, float *dec_out, void *stream_)
 {
     if (int rc = check_desc(d)) return rc;
     GA_REQUIRE(params && geo_nchw && workspace && dec_out, "NULL pointer argument");
+    const int frames = d->frames ? d->frames : 1;
+    GA_REQUIRE(frames == 1 || pose_feat_nchw, "frames > 1 needs the per-frame pose feature maps");
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const Layout L = make_layout();
-    const Workspace w = carve_ws(workspace, d->S, d->feat_res);
+    const Workspace w = carve_ws(workspace, d->S, d->feat_res, frames);
     const Coef cf = coef_views(w);
     const int S = d->S, Hf = d->feat_res, P = Hf * Hf;
-    const int M = S * S;
+    const int M = frames * S * S;                    // decoder rows: every frame's UV pixels (stage 1: one shared frame)
 
     {
         ProfScope _ps("chw_to_hwc_kernel", st);
@@ -586,9 +622,18 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
             if (int rc = launch_gemm<128, 64>("geom_conv_fwd", A, B, E, P, kCg, 25 * kCg, 1, st)) return rc;
         }
     }
+    const float *Fsrc = w.F[3];
+    size_t fstride = 0;
+    if (pose_feat_nchw) {          // stage 2: pix_feature = pose_featmap + geom_featmap (model/network.py:58), one map per frame
+        ProfScope _ps("chw_to_hwc_add_kernel", st);
+        float *Fp = frames > 1 ? w.Fp : w.F[3];
+        chw_to_hwc_add_kernel<<<dim3(cdiv(P, 64), frames), 256, 0, st>>>(pose_feat_nchw, w.F[3], Fp, P);
+        Fsrc = Fp; fstride = frames > 1 ? (size_t)P * kCg : 0;
+    }
+    if (pose_feat_nchw) GA_CHECK_LAUNCH("chw_to_hwc_add_kernel");
     {
         ProfScope _ps("sample_feat_fwd_kernel", st);
-        sample_feat_fwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, w.F[3], w.feat);
+        sample_feat_fwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, frames, fstride, Fsrc, w.feat);
     }
     GA_CHECK_LAUNCH("sample_feat_fwd_kernel");
     GA_CHECK_CUDA(cudaMemsetAsync(w.stat, 0, sizeof(double) * 2 * kBnCh, st));
@@ -598,7 +643,7 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
         const int o = kBnOff[l];
         {
             ProfScope _ps("bn_finalize_fwd_kernel", st);
-            bn_finalize_fwd_kernel<<<cdiv(C, 128), 128, 0, st>>>(C, (double)M, (double)M * d->batch, d->bn_eps, d->bn_momentum, sum + o, sumsq + o,
+            bn_finalize_fwd_kernel<<<cdiv(C, 128), 128, 0, st>>>(C, (double)M, (double)S * S * d->batch, d->bn_eps, d->bn_momentum, sum + o, sumsq + o,
                                                                  params + L.gamma[l] , params + L.beta[l], cf.mean + o, cf.rstd + o, cf.a + o, cf.b + o,
                                                                  bn_running ? bn_running + o : nullptr, bn_running ? bn_running + kBnCh + o : nullptr);
         }
@@ -678,16 +723,18 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
 }
 
 extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, void *workspace, const float *dec_out,
-                                   const float *d_dec_out, float *d_params, float *d_geo_nchw, void *stream_)
+                                   const float *d_dec_out, float *d_params, float *d_geo_nchw, float *d_pose_feat_nchw, void *stream_)
 {
     if (int rc = check_desc(d)) return rc;
     GA_REQUIRE(params && workspace && dec_out && d_dec_out && d_params && d_geo_nchw, "NULL pointer argument");
+    const int frames = d->frames ? d->frames : 1;
+    GA_REQUIRE(frames == 1 || d_pose_feat_nchw, "frames > 1 needs d_pose_feat_nchw");
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const Layout L = make_layout();
-    const Workspace w = carve_ws(workspace, d->S, d->feat_res);
+    const Workspace w = carve_ws(workspace, d->S, d->feat_res, frames);
     const Coef cf = coef_views(w);
     const int S = d->S, Hf = d->feat_res, P = Hf * Hf;
-    const int M = S * S;
+    const int M = frames * S * S;
     const int kSplit = 2 * kNumSMs;   // split-K CTAs of a 128x128 weight-gradient tile
 
     GA_CHECK_CUDA(cudaMemsetAsync(d_params, 0, sizeof(float) * (size_t)L.total, st));
@@ -851,12 +898,26 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         if (int rc = launch_gemm<128, 128>("mlp_dgrad_l1", A2, B2, E2, M, kFeatLd, kH, 1, st)) return rc;
     }
     // up-sampling backward, then the three convs
-    GA_CHECK_CUDA(cudaMemsetAsync(w.dF[0], 0, sizeof(float) * (size_t)P * kCg, st));
+    float *dsink = frames > 1 ? w.dFp : w.dF[0];
+    GA_CHECK_CUDA(cudaMemsetAsync(dsink, 0, sizeof(float) * (size_t)frames * P * kCg, st));
     {
         ProfScope _ps("sample_feat_bwd_kernel", st);
-        sample_feat_bwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, w.d_feat, w.dF[0]);
+        sample_feat_bwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, frames, frames > 1 ? (size_t)P * kCg : 0, w.d_feat, dsink);
     }
     GA_CHECK_LAUNCH("sample_feat_bwd_kernel");
+    if (d_pose_feat_nchw) {        // d pose_featmap[f] = d pix[f] (NCHW); d geom_featmap = sum over the frames
+        for (int f = 0; f < frames; ++f) {
+            ProfScope _ps("hwc_to_chw_kernel", st);
+            hwc_to_chw_kernel<<<cdiv(P, 64), 256, 0, st>>>(dsink + (size_t)f * P * kCg, d_pose_feat_nchw + (size_t)f * P * kCg, P);
+            GA_CHECK_LAUNCH("hwc_to_chw_kernel");
+        }
+    }
+    if (frames > 1) {
+        ProfScope _ps("sum_frames_kernel", st);
+        sum_frames_kernel<<<cdiv((long long)P * kCg / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(w.dFp), reinterpret_cast<float4 *>(w.dF[0]),
+                                                                            (size_t)P * kCg / 4, frames);
+    }
+    if (frames > 1) GA_CHECK_LAUNCH("sum_frames_kernel");
     float *dcur = w.dF[0], *dnxt = w.dF[1];
     if (d->flags & GA_DECODER_TENSOR_CORES) {
         // the forward pass left F[0..2] and the weight copy TF32-rounded; the up-sampling gradient is rounded in place (it only
@@ -896,7 +957,7 @@ extern "C" int ga_decoder_views(const GaDecoderDesc *d, void *workspace, GaDecod
 {
     if (int rc = check_desc(d)) return rc;
     GA_REQUIRE(workspace && out, "NULL pointer argument");
-    const Workspace w = carve_ws(workspace, d->S, d->feat_res);
+    const Workspace w = carve_ws(workspace, d->S, d->feat_res, d->frames ? d->frames : 1);
     const Coef cf = coef_views(w);
     out->conv3_nhwc = w.F[3];
     out->feat = w.feat;

@@ -62,7 +62,8 @@ struct alignas(128) LbsSmem {
 
 template <bool kBackward>
 __global__ void __launch_bounds__(kTileN)
-lbs_kernel(int N, int B, float scale_mul, const float *__restrict__ dec /*[S*S,8]*/, const int32_t *__restrict__ vidx,
+lbs_kernel(int N, int B, float scale_mul, long long dec_stride /*floats between two frames' decoder outputs; 0: one output shared by all*/,
+           const float *__restrict__ dec /*[S*S,8] or [B][S*S,8]*/, const int32_t *__restrict__ vidx,
            const float *__restrict__ q /*[N,3]*/, const float *__restrict__ w /*[N,24]*/,
            const float *__restrict__ Cg /*[B,24,12]*/,
            // forward outputs
@@ -130,6 +131,12 @@ lbs_kernel(int N, int B, float scale_mul, const float *__restrict__ dec /*[S*S,8
         }
         float dcx = 0.f, dcy = 0.f, dcz = 0.f, dsc = 0.f, dr = 0.f, dg = 0.f, dbl = 0.f;
         for (int b = 0; b < B; ++b) {
+            if (dec_stride && valid) {          // stage 2: every frame has its own decoder output
+                const float *db = dec + (size_t)b * dec_stride + (size_t)vi * 8;
+                const float4 o0 = *reinterpret_cast<const float4 *>(db), o1 = *reinterpret_cast<const float4 *>(db + 4);
+                cx = q[(size_t)n * 3] + 0.02f * o0.x; cy = q[(size_t)n * 3 + 1] + 0.02f * o0.y; cz = q[(size_t)n * 3 + 2] + 0.02f * o0.z;
+                sc = o0.w * scale_mul; r = o1.x; g = o1.y; bl = o1.z;
+            }
             float M[12];
 #pragma unroll
             for (int e = 0; e < 12; ++e) M[e] = 0.f;
@@ -177,9 +184,17 @@ lbs_kernel(int N, int B, float scale_mul, const float *__restrict__ dec /*[S*S,8
                         acc[b][h] += t;
                     }
                 }
+                if (dec_stride) {               // per-frame decoder output: this frame's gradient goes to this frame's rows
+                    if (valid) {
+                        float *db = d_dec + (size_t)b * dec_stride + (size_t)vi * 8;
+                        *reinterpret_cast<float4 *>(db) = make_float4(0.02f * dcx, 0.02f * dcy, 0.02f * dcz, scale_mul * dsc);
+                        *reinterpret_cast<float4 *>(db + 4) = make_float4(dr, dg, dbl, 0.f);
+                    }
+                    dcx = dcy = dcz = dsc = dr = dg = dbl = 0.f;
+                }
             }
         }
-        if (kBackward && valid) {
+        if (kBackward && valid && !dec_stride) {
             float4 o0 = make_float4(0.02f * dcx, 0.02f * dcy, 0.02f * dcz, scale_mul * dsc);
             float4 o1 = make_float4(dr, dg, dbl, 0.f);
             *reinterpret_cast<float4 *>(d_dec + (size_t)vi * 8) = o0;
@@ -208,7 +223,7 @@ int launch_cfg(int N)
 
 using namespace ga;
 
-extern "C" int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, const float *dec_out, const int32_t *valid_index,
+extern "C" int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, int64_t dec_frame_stride, const float *dec_out, const int32_t *valid_index,
                               const float *query_points, const float *query_lbs, const float *cano2live, float *means3D,
                               float *scales3, float *colors, void *stream_)
 {
@@ -222,13 +237,13 @@ extern "C" int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, const float
         attr_set = true;
     }
     { ProfScope _ps("lbs_kernel<fwd>", static_cast<cudaStream_t>(stream_)); lbs_kernel<false><<<launch_cfg(N), kTileN, sizeof(LbsSmem), static_cast<cudaStream_t>(stream_)>>>(
-        N, B, scale_mul, dec_out, valid_index, query_points, query_lbs, cano2live, means3D, scales3, colors, nullptr, nullptr,
+        N, B, scale_mul, (long long)dec_frame_stride, dec_out, valid_index, query_points, query_lbs, cano2live, means3D, scales3, colors, nullptr, nullptr,
         nullptr, nullptr, nullptr); }
     GA_CHECK_LAUNCH("lbs_kernel<fwd>");
     return GA_OK;
 }
 
-extern "C" int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float scale_mul, const float *dec_out,
+extern "C" int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float scale_mul, int64_t dec_frame_stride, const float *dec_out,
                                const int32_t *valid_index, const float *query_points, const float *query_lbs,
                                const float *cano2live, const float *d_means3D, const float *d_scales3, const float *d_colors,
                                float *d_dec_out, float *d_cano2live, void *stream_)
@@ -245,7 +260,7 @@ extern "C" int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float s
         GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
         attr_set = true;
     }
-    { ProfScope _ps("lbs_kernel<bwd>", stream); lbs_kernel<true><<<launch_cfg(N), kTileN, sizeof(LbsSmem), stream>>>(N, B, scale_mul, dec_out, valid_index, query_points,
+    { ProfScope _ps("lbs_kernel<bwd>", stream); lbs_kernel<true><<<launch_cfg(N), kTileN, sizeof(LbsSmem), stream>>>(N, B, scale_mul, (long long)dec_frame_stride, dec_out, valid_index, query_points,
                                                                         query_lbs, cano2live, nullptr, nullptr, nullptr,
                                                                         d_means3D, d_scales3, d_colors, d_dec_out, d_cano2live); }
     GA_CHECK_LAUNCH("lbs_kernel<bwd>");

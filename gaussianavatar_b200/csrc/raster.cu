@@ -176,28 +176,14 @@ struct CamSrc {
     float tanx, tany;
 };
 
-// K1: one thread per Gaussian (blockIdx.y = frame).  Besides the per-Gaussian state it counts, per tile, the instances the
-// tile will receive (tile_count[frame][tile]): the binning that follows is a bucket sort by tile, not a global sort.
-__global__ void __launch_bounds__(256)
-preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, CamSrc cam, float mod, const float *__restrict__ means3D,
-                      const float *__restrict__ scales, const float *__restrict__ rots, long long rot_stride,
-                      const float *__restrict__ opac, long long opac_stride, float *__restrict__ depth,
-                      float2 *__restrict__ xy, float4 *__restrict__ conic_o, float *__restrict__ cov3d,
-                      uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect, int32_t *__restrict__ radii,
-                      uint32_t *__restrict__ tile_count)
+// Per-Gaussian part of K1; returns the tile rect (zero area if the Gaussian is culled).
+__device__ __forceinline__ ushort4
+preprocess_one(int il, size_t i, int H, int W, int gx, int gy, const float *view, const float *proj, float tanfovx, float tanfovy,
+               float mod, const float *__restrict__ means3D, const float *__restrict__ scales, const float *__restrict__ rq,
+               float opacity, float *__restrict__ depth, float2 *__restrict__ xy, float4 *__restrict__ conic_o,
+               float *__restrict__ cov3d, uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect, int32_t *__restrict__ radii)
 {
-    const int b = blockIdx.y;
-    __shared__ float view[16], proj[16];
-    if (threadIdx.x < 16) view[threadIdx.x] = cam.view[(size_t)b * cam.stride + threadIdx.x];
-    else if (threadIdx.x < 32) proj[threadIdx.x - 16] = cam.proj[(size_t)b * cam.stride + threadIdx.x - 16];
-    __syncthreads();
-    const float tanfovx = cam.tan ? cam.tan[(size_t)b * cam.stride] : cam.tanx;
-    const float tanfovy = cam.tan ? cam.tan[(size_t)b * cam.stride + 1] : cam.tany;
-    const int il = blockIdx.x * blockDim.x + threadIdx.x;
-    if (il >= P) return;
-    const size_t i = (size_t)b * P + il;
-    const float *rq = rots + (size_t)b * rot_stride + 4 * (size_t)il;
-
+    const ushort4 none = make_ushort4(0, 0, 0, 0);
     radii[i] = 0;
     tiles[i] = 0;
     depth[i] = 0.f;
@@ -209,7 +195,7 @@ preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, CamSrc cam, float mod
 
     const float px = means3D[3 * (size_t)i], py = means3D[3 * (size_t)i + 1], pz = means3D[3 * (size_t)i + 2];
     const float tvx = xf_row(view, 0, px, py, pz), tvy = xf_row(view, 1, px, py, pz), tvz = xf_row(view, 2, px, py, pz);
-    if (tvz <= 0.2f) return;
+    if (tvz <= 0.2f) return none;
 
     const float hx = xf_row(proj, 0, px, py, pz), hy = xf_row(proj, 1, px, py, pz), hw = xf_row(proj, 3, px, py, pz);
     const float p_w = div_(1.f, add_(hw, 0.0000001f));
@@ -260,7 +246,7 @@ preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, CamSrc cam, float mod
     const float cc = add_(fma_(m1[2], v12, fma_(m1[1], v11, mul_(m1[0], v10))), 0.3f);
 
     const float det = sub_(mul_(ca, cc), mul_(cb, cb));
-    if (det == 0.f) return;
+    if (det == 0.f) return none;
     const float det_inv = div_(1.f, det);
     const float conx = mul_(cc, det_inv), cony = mul_(-cb, det_inv), conz = mul_(ca, det_inv);
     const float mid = mul_(0.5f, add_(ca, cc));
@@ -277,19 +263,107 @@ preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, CamSrc cam, float mod
     int rmaxx = __float2int_rz(div_(add_(add_(pixx, rf), 15.f), 16.f)); rmaxx = min(gx, max(0, rmaxx));
     int rmaxy = __float2int_rz(div_(add_(add_(pixy, rf), 15.f), 16.f)); rmaxy = min(gy, max(0, rmaxy));
     const int area = (rmaxx - rminx) * (rmaxy - rminy);
-    if (area == 0) return;
+    if (area == 0) return none;
 
     float *c3 = cov3d + 6 * (size_t)i;
     c3[0] = S00; c3[1] = S01; c3[2] = S02; c3[3] = S11; c3[4] = S12; c3[5] = S22;
     depth[i] = tvz;
     radii[i] = radius;
     xy[i] = make_float2(pixx, pixy);
-    conic_o[i] = make_float4(conx, cony, conz, opac[(size_t)b * opac_stride + il]);
+    conic_o[i] = make_float4(conx, cony, conz, opacity);
     tiles[i] = (uint32_t)area;
-    rect[i] = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx, (unsigned short)rmaxy);
+    const ushort4 rc = make_ushort4((unsigned short)rminx, (unsigned short)rminy, (unsigned short)rmaxx, (unsigned short)rmaxy);
+    rect[i] = rc;
+    return rc;
+}
+
+// Visit every tile of every lane's rect with op(tile, payload-of-the-owning-lane), load-balanced inside the warp: a Gaussian that
+// touches a few tiles (the rule) is handled by its own lane; one that touches many (large radius: a serial loop of dependent atomics
+// that used to set the kernel's duration) is spread over the 32 lanes, 32 tiles per step.
+template <class Op>
+__device__ __forceinline__ void for_each_tile_balanced(const ushort4 rc, int gx, uint64_t payload, Op op)
+{
+    constexpr int kSmall = 4;
+    const int lane = threadIdx.x & 31;
+    const int w = (int)rc.z - (int)rc.x, area = w * ((int)rc.w - (int)rc.y);
+    if (area <= kSmall)
+        for (int k = 0; k < area; ++k) op((uint32_t)(((int)rc.y + k / w) * gx + (int)rc.x + k % w), payload);
+    uint32_t big = __ballot_sync(0xffffffffu, area > kSmall);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const int x0 = __shfl_sync(0xffffffffu, (int)rc.x, src), y0 = __shfl_sync(0xffffffffu, (int)rc.y, src);
+        const int ws = __shfl_sync(0xffffffffu, w, src), as = __shfl_sync(0xffffffffu, area, src);
+        const uint64_t pl = __shfl_sync(0xffffffffu, payload, src);
+        for (int k = lane; k < as; k += 32) op((uint32_t)((y0 + k / ws) * gx + x0 + k % ws), pl);
+    }
+}
+
+// The tile bounding box of a CTA's rects (x0, y0, width, height in tiles; width = 0 if every rect is empty), through shared memory.
+constexpr int kHistTiles = 10240;    // tiles a CTA-local histogram covers (40 KB): a CTA's 256 Gaussians are neighbours on screen
+__device__ __forceinline__ int4 cta_tile_bbox(const ushort4 rc, uint32_t *s_box /*[4]*/)
+{
+    if (threadIdx.x == 0) { s_box[0] = 0xffffu; s_box[1] = 0xffffu; s_box[2] = 0u; s_box[3] = 0u; }
+    __syncthreads();
+    uint32_t x0 = 0xffffu, y0 = 0xffffu, x1 = 0u, y1 = 0u;
+    if (rc.z > rc.x && rc.w > rc.y) { x0 = rc.x; y0 = rc.y; x1 = rc.z; y1 = rc.w; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if ((threadIdx.x & 31) == 0 && x1 > x0) { atomicMin(&s_box[0], x0); atomicMin(&s_box[1], y0); atomicMax(&s_box[2], x1); atomicMax(&s_box[3], y1); }
+    __syncthreads();
+    const int bx0 = (int)s_box[0], by0 = (int)s_box[1], bx1 = (int)s_box[2], by1 = (int)s_box[3];
+    return bx1 > bx0 ? make_int4(bx0, by0, bx1 - bx0, by1 - by0) : make_int4(0, 0, 0, 0);
+}
+
+// K1: one thread per Gaussian (blockIdx.y = frame).  Besides the per-Gaussian state it counts, per tile, the instances the
+// tile will receive (tile_count[frame][tile]): the binning that follows is a bucket sort by tile, not a global sort.
+// The CTA's 256 Gaussians (neighbours in UV space, so neighbours on screen) first count into a shared-memory histogram over their
+// common tile bounding box and then add only its non-zero bins to the global counters — a few hundred thousand atomics on a few
+// hundred hot addresses (which serialise in L2 and used to set this kernel's duration) become a few tens per CTA.  A CTA whose
+// bounding box exceeds the histogram (huge Gaussians) counts straight into global memory.
+template <bool kSmemHist>
+__global__ void __launch_bounds__(256)
+preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, CamSrc cam, float mod, const float *__restrict__ means3D,
+                      const float *__restrict__ scales, const float *__restrict__ rots, long long rot_stride,
+                      const float *__restrict__ opac, long long opac_stride, float *__restrict__ depth,
+                      float2 *__restrict__ xy, float4 *__restrict__ conic_o, float *__restrict__ cov3d,
+                      uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect, int32_t *__restrict__ radii,
+                      uint32_t *__restrict__ tile_count)
+{
+    const int b = blockIdx.y;
+    __shared__ float view[16], proj[16];
+    if (threadIdx.x < 16) view[threadIdx.x] = cam.view[(size_t)b * cam.stride + threadIdx.x];
+    else if (threadIdx.x < 32) proj[threadIdx.x - 16] = cam.proj[(size_t)b * cam.stride + threadIdx.x - 16];
+    __syncthreads();
+    const float tanfovx = cam.tan ? cam.tan[(size_t)b * cam.stride] : cam.tanx;
+    const float tanfovy = cam.tan ? cam.tan[(size_t)b * cam.stride + 1] : cam.tany;
+    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    ushort4 rc = make_ushort4(0, 0, 0, 0);
+    if (il < P)
+        rc = preprocess_one(il, (size_t)b * P + il, H, W, gx, gy, view, proj, tanfovx, tanfovy, mod, means3D, scales,
+                            rots + (size_t)b * rot_stride + 4 * (size_t)il, opac[(size_t)b * opac_stride + il], depth, xy, conic_o, cov3d,
+                            tiles, rect, radii);
     uint32_t *tc = tile_count + (size_t)b * gx * gy;
-    for (int y = rminy; y < rmaxy; ++y)
-        for (int x = rminx; x < rmaxx; ++x) atomicAdd(&tc[y * gx + x], 1u);
+    __shared__ uint32_t s_hist[kHistTiles], s_box[4];
+    const int4 box = cta_tile_bbox(rc, s_box);
+    const int area = box.z * box.w;
+    if (kSmemHist && area > 0 && area <= kHistTiles) {
+        for (int t = threadIdx.x; t < area; t += blockDim.x) s_hist[t] = 0u;
+        __syncthreads();
+        for_each_tile_balanced(rc, gx, 0ull, [&](uint32_t tile, uint64_t) {
+            atomicAdd(&s_hist[((int)tile / gx - box.y) * box.z + (int)tile % gx - box.x], 1u);
+        });
+        __syncthreads();
+        for (int t = threadIdx.x; t < area; t += blockDim.x) {
+            const uint32_t c = s_hist[t];
+            if (c) atomicAdd(&tc[(box.y + t / box.z) * gx + box.x + t % box.z], c);
+        }
+    } else {
+        for_each_tile_balanced(rc, gx, 0ull, [&](uint32_t tile, uint64_t) { atomicAdd(&tc[tile], 1u); });
+    }
 }
 
 // K2: ONE CTA scans the per-tile instance counts of all frames: tile ranges (global offsets into the instance arrays; untouched
@@ -310,24 +384,33 @@ tile_scan_kernel(int n, int T, long long capacity, const uint32_t *__restrict__ 
     if (threadIdx.x == 0) { carry_c = 0; carry_s = 0; }
     if (threadIdx.x < 33) cls_count[threadIdx.x] = 0;
     __syncthreads();
-    for (int base = 0; base < n; base += 1024) {
-        const int i = base + threadIdx.x;
-        const unsigned long long c = i < n ? count[i] : 0ull;
-        unsigned long long ex, tot;
+    constexpr int kItems = 4;                       // tiles per thread per round: 4096 tiles per round
+    for (int base = 0; base < n; base += 1024 * kItems) {
+        unsigned long long c[kItems], ex[kItems], segs[kItems], sex[kItems], tot, stot;
+        bool fits[kItems];
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) { const int i = base + threadIdx.x * kItems + k; c[k] = i < n ? count[i] : 0ull; }
         Scan(tmp).ExclusiveSum(c, ex, tot);
-        const unsigned long long pos = carry_c + ex, end = pos + c;
-        const bool fits = end <= (unsigned long long)capacity;
-        const unsigned long long segs = (fits && c) ? (c + kSeg - 1) / kSeg : 0ull;
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const unsigned long long end = carry_c + ex[k] + c[k];
+            fits[k] = end <= (unsigned long long)capacity;
+            segs[k] = (fits[k] && c[k]) ? (c[k] + kSeg - 1) / kSeg : 0ull;
+        }
         __syncthreads();
-        unsigned long long sex, stot;
         Scan(tmp).ExclusiveSum(segs, sex, stot);
-        if (i < n) {
-            ranges[i] = (fits && c) ? make_uint2((uint32_t)pos, (uint32_t)end) : make_uint2(0u, 0u);
-            cursor[i] = (uint32_t)(pos < 0xffffffffull ? pos : 0xffffffffull);
-            seg_start[i] = (uint32_t)(carry_s + sex);
-            if (i % T == 0) status[4 + i / T] = (int32_t)(pos < 0x7fffffffull ? pos : 0x7fffffffull);
-            // class 0: empty (or not fitting) tiles, class k >= 1: 2^(k-1) <= count < 2^k
-            atomicAdd(&cls_count[(fits && c) ? 32 - __clz((uint32_t)c) : 0], 1u);
+#pragma unroll
+        for (int k = 0; k < kItems; ++k) {
+            const int i = base + threadIdx.x * kItems + k;
+            if (i < n) {
+                const unsigned long long pos = carry_c + ex[k], end = pos + c[k];
+                ranges[i] = (fits[k] && c[k]) ? make_uint2((uint32_t)pos, (uint32_t)end) : make_uint2(0u, 0u);
+                cursor[i] = (uint32_t)(pos < 0xffffffffull ? pos : 0xffffffffull);
+                seg_start[i] = (uint32_t)(carry_s + sex[k]);
+                if (i % T == 0) status[4 + i / T] = (int32_t)(pos < 0x7fffffffull ? pos : 0x7fffffffull);
+                // class 0: empty (or not fitting) tiles, class k >= 1: 2^(k-1) <= count < 2^k
+                atomicAdd(&cls_count[(fits[k] && c[k]) ? 32 - __clz((uint32_t)c[k]) : 0], 1u);
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) { carry_c += tot; carry_s += stot; }
@@ -351,7 +434,10 @@ tile_scan_kernel(int n, int T, long long capacity, const uint32_t *__restrict__ 
     }
 }
 
-// K3: one thread per Gaussian drops (depth bits << 32 | index) into the bucket of every tile its rect touches.
+// K3: one thread per Gaussian drops (depth bits << 32 | index) into the bucket of every tile its rect touches (large rects are
+// spread over the warp, see for_each_tile_balanced).  kSmemHist: as in K1 the CTA counts into shared memory first, reserves ONE
+// contiguous run per touched tile with a single global atomic, and hands out the places inside the run with shared-memory atomics.
+template <bool kSmemHist>
 __global__ void __launch_bounds__(256)
 bucket_scatter_kernel(int P, int gx, int T, long long capacity, const float *__restrict__ depth,
                       const uint32_t *__restrict__ tiles, const ushort4 *__restrict__ rect, uint32_t *__restrict__ cursor,
@@ -359,17 +445,40 @@ bucket_scatter_kernel(int P, int gx, int T, long long capacity, const float *__r
 {
     const int b = blockIdx.y;
     const int il = blockIdx.x * blockDim.x + threadIdx.x;
-    if (il >= P) return;
-    const size_t i = (size_t)b * P + il;
-    if (tiles[i] == 0) return;
-    const uint64_t key = ((uint64_t)__float_as_uint(depth[i]) << 32) | (uint32_t)il;
-    const ushort4 r = rect[i];
-    uint32_t *cur = cursor + (size_t)b * T;
-    for (int y = r.y; y < r.w; ++y)
-        for (int x = r.x; x < r.z; ++x) {
-            const uint32_t pos = atomicAdd(&cur[y * gx + x], 1u);
-            if ((long long)pos < capacity) bucket[pos] = key;
+    ushort4 rc = make_ushort4(0, 0, 0, 0);
+    uint64_t key = 0;
+    if (il < P) {
+        const size_t i = (size_t)b * P + il;
+        if (tiles[i] != 0) {
+            rc = rect[i];
+            key = ((uint64_t)__float_as_uint(depth[i]) << 32) | (uint32_t)il;
         }
+    }
+    uint32_t *cur = cursor + (size_t)b * T;
+    __shared__ uint32_t s_hist[kHistTiles], s_box[4];          // counts, then the next place inside the CTA's run of each tile
+    const int4 box = cta_tile_bbox(rc, s_box);
+    const int area = box.z * box.w;
+    if (kSmemHist && area > 0 && area <= kHistTiles) {
+        auto local = [&](uint32_t tile) { return ((int)tile / gx - box.y) * box.z + (int)tile % gx - box.x; };
+        for (int t = threadIdx.x; t < area; t += blockDim.x) s_hist[t] = 0u;
+        __syncthreads();
+        for_each_tile_balanced(rc, gx, 0ull, [&](uint32_t tile, uint64_t) { atomicAdd(&s_hist[local(tile)], 1u); });
+        __syncthreads();
+        for (int t = threadIdx.x; t < area; t += blockDim.x) {
+            const uint32_t c = s_hist[t];
+            if (c) s_hist[t] = atomicAdd(&cur[(box.y + t / box.z) * gx + box.x + t % box.z], c);
+        }
+        __syncthreads();
+        for_each_tile_balanced(rc, gx, key, [&](uint32_t tile, uint64_t k) {
+            const uint32_t pos = atomicAdd(&s_hist[local(tile)], 1u);
+            if ((long long)pos < capacity) bucket[pos] = k;
+        });
+    } else {
+        for_each_tile_balanced(rc, gx, key, [&](uint32_t tile, uint64_t k) {
+            const uint32_t pos = atomicAdd(&cur[tile], 1u);
+            if ((long long)pos < capacity) bucket[pos] = k;
+        });
+    }
 }
 
 // Squared distance from a Gaussian's centre beyond which it is certain that the compositing loop skips it
@@ -426,6 +535,9 @@ tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const
                  uint32_t *__restrict__ tile_maxc)
 {
     extern __shared__ uint64_t s_keys[];
+    using BinScan = cub::BlockScan<uint32_t, kSortThreads>;
+    __shared__ typename BinScan::TempStorage s_scan;
+    __shared__ uint32_t s_hist[1025], s_off[1025], s_red[3];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BT; i += gridDim.x * blockDim.x) tile_maxc[i] = 0u;
     const int nactive = status[3];
     for (int it = blockIdx.x; it < nactive; it += gridDim.x) {
@@ -448,11 +560,69 @@ tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const
         };
 
         if (n <= kSortMax) {
-            int n2 = 32;
-            while (n2 < n) n2 <<= 1;
-            for (int i = threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = i < n ? bucket[r.x + i] : ~0ull;
-            __syncthreads();
-            bitonic_sort_smem(s_keys, n2);
+            // Bucket-then-insertion: one counting pass over linear depth bins (about 8 entries each) puts every key within a few
+            // places of its final position, one thread per bin finishes it by insertion — a fraction of the shared-memory traffic of
+            // a full bitonic network.  Bins are monotone in depth, ties inside a bin are ordered by the full (depth bits, index) key,
+            // so the result is the same total order.  Degenerate depth distributions (a bin above kMaxBin entries, e.g. many
+            // equal depths) fall back to the bitonic network on the same buffer.
+            constexpr int kMaxBin = 48;
+            const int nb = n >= 64 ? min(1024, max(32, n >> 3)) : 0;
+            bool binned = false;
+            if (nb) {
+                uint32_t lo = 0xffffffffu, hi = 0u;
+                for (int i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t d = (uint32_t)(bucket[r.x + i] >> 32); lo = min(lo, d); hi = max(hi, d); }
+                for (int i = threadIdx.x; i < 1025; i += blockDim.x) s_hist[i] = 0;
+                if (threadIdx.x == 0) { s_red[0] = 0xffffffffu; s_red[1] = 0u; s_red[2] = 0u; }
+                __syncthreads();
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+                if ((threadIdx.x & 31) == 0) { atomicMin(&s_red[0], lo); atomicMax(&s_red[1], hi); }
+                __syncthreads();
+                const float dmin = __uint_as_float(s_red[0]), dmax = __uint_as_float(s_red[1]);      // depths are positive: bit order = value order
+                if (dmax > dmin) {
+                    const float scale = (float)nb / (dmax - dmin);
+                    auto bin_of = [&](uint64_t key) { return min(nb - 1, (int)((__uint_as_float((uint32_t)(key >> 32)) - dmin) * scale)); };
+                    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[bin_of(bucket[r.x + i])], 1u);
+                    __syncthreads();
+                    // exclusive scan of the bin counts (nb <= 1024 <= 2 per thread) and their maximum
+                    uint32_t c0 = 2 * threadIdx.x < nb ? s_hist[2 * threadIdx.x] : 0u, c1 = 2 * threadIdx.x + 1 < nb ? s_hist[2 * threadIdx.x + 1] : 0u;
+                    uint32_t ex;
+                    BinScan(s_scan).ExclusiveSum(c0 + c1, ex);
+                    if (max(c0, c1) > kMaxBin) s_red[2] = 1u;
+                    __syncthreads();
+                    if (2 * threadIdx.x < nb) { s_off[2 * threadIdx.x] = ex; s_hist[2 * threadIdx.x] = ex; }
+                    if (2 * threadIdx.x + 1 < nb) { s_off[2 * threadIdx.x + 1] = ex + c0; s_hist[2 * threadIdx.x + 1] = ex + c0; }
+                    if (threadIdx.x == 0) s_off[nb] = (uint32_t)n;
+                    __syncthreads();
+                    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                        const uint64_t key = bucket[r.x + i];
+                        s_keys[atomicAdd(&s_hist[bin_of(key)], 1u)] = key;
+                    }
+                    __syncthreads();
+                    if (s_red[2] == 0u) {
+                        for (int bi = threadIdx.x; bi < nb; bi += blockDim.x) {
+                            const int b0 = (int)s_off[bi], b1 = (int)s_off[bi + 1];
+                            for (int i = b0 + 1; i < b1; ++i) {
+                                const uint64_t key = s_keys[i];
+                                int j = i - 1;
+                                while (j >= b0 && s_keys[j] > key) { s_keys[j + 1] = s_keys[j]; --j; }
+                                s_keys[j + 1] = key;
+                            }
+                        }
+                        __syncthreads();
+                        binned = true;
+                    }
+                }
+            }
+            if (!binned) {
+                int n2 = 32;
+                while (n2 < n) n2 <<= 1;
+                if (!nb || !(__uint_as_float(s_red[1]) > __uint_as_float(s_red[0])))          // s_keys not filled by the scatter pass
+                    for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = bucket[r.x + i];
+                for (int i = n + threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = ~0ull;
+                __syncthreads();
+                bitonic_sort_smem(s_keys, n2);
+            }
             for (int i = threadIdx.x; i < n; i += blockDim.x) emit(i, s_keys[i]);
             __syncthreads();                 // s_keys is reloaded by the next tile
             continue;
@@ -934,9 +1104,9 @@ int launch_preprocess(const Dims &d, const CamSrc &cam, const FwdArgs &a, long l
     GA_CHECK_CUDA(cudaMemsetAsync(iv.count, 0, sizeof(uint32_t) * BT, stream));
     if (d.P > 0) {
         ProfScope _ps("preprocess_fwd_kernel", stream);
-        preprocess_fwd_kernel<<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.H, d.W, d.gx, d.gy, cam, a.mod, a.means3D, a.scales,
-                                                                            a.rotations, a.rot_stride, a.opacities, a.opac_stride, g.depth,
-                                                                            g.xy, g.conic_o, g.cov3d, g.tiles, g.rect, radii, iv.count);
+        preprocess_fwd_kernel<true><<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.H, d.W, d.gx, d.gy, cam, a.mod, a.means3D, a.scales,
+                                                                                  a.rotations, a.rot_stride, a.opacities, a.opac_stride, g.depth,
+                                                                                  g.xy, g.conic_o, g.cov3d, g.tiles, g.rect, radii, iv.count);
         GA_CHECK_LAUNCH("preprocess_fwd_kernel");
     }
     {
@@ -960,8 +1130,8 @@ int launch_binning_and_render(const Dims &d, const FwdArgs &a, long long capacit
     if (d.P > 0) {
         {
             ProfScope _ps("bucket_scatter_kernel", stream);
-            bucket_scatter_kernel<<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.gx, d.T, capacity, g.depth, g.tiles, g.rect, iv.cursor,
-                                                                                bv.bucket);
+            bucket_scatter_kernel<true><<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.gx, d.T, capacity, g.depth, g.tiles, g.rect, iv.cursor,
+                                                                                      bv.bucket);
         }
         GA_CHECK_LAUNCH("bucket_scatter_kernel");
     }

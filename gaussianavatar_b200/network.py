@@ -34,9 +34,9 @@ _BN_LAYERS = ["bn1", "bn2", "bn3", "bn4", "bn5", "bn6", "bn6N", "bn6SH", "bn7", 
 class DecoderState:
     """Device-side state of one decoder instance: descriptor, activation workspace, BatchNorm running statistics."""
 
-    def __init__(self, S: int, feat_res: int, batch: int, device, c_geom=64, hsize=128, eps=1e-5, momentum=0.1, tensor_cores=True):
+    def __init__(self, S: int, feat_res: int, batch: int, device, c_geom=64, hsize=128, eps=1e-5, momentum=0.1, tensor_cores=True, frames=1):
         self.desc = _lib.GaDecoderDesc(int(S), int(feat_res), int(batch), int(c_geom), int(hsize), float(eps), float(momentum),
-                                       1 if tensor_cores else 0)
+                                       1 if tensor_cores else 0, int(frames))
         nbytes = _lib.lib().ga_decoder_workspace_bytes(ctypes.byref(self.desc))
         if nbytes == 0:
             raise RuntimeError("ga_decoder_workspace_bytes failed: " + _lib.lib().ga_last_error().decode())
@@ -47,7 +47,7 @@ class DecoderState:
 
 
 def decoder_layout(c_geom=64, hsize=128) -> _lib.GaDecoderLayout:
-    desc = _lib.GaDecoderDesc(2, 1, 1, c_geom, hsize, 1e-5, 0.1, 0)
+    desc = _lib.GaDecoderDesc(2, 1, 1, c_geom, hsize, 1e-5, 0.1, 0, 1)
     lay = _lib.GaDecoderLayout()
     _lib.check(_lib.lib().ga_decoder_layout(ctypes.byref(desc), ctypes.byref(lay)), "ga_decoder_layout")
     return lay
@@ -200,11 +200,11 @@ class POP_no_unet(nn.Module):
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     # ---- execution ------------------------------------------------------------------------------------------------
-    def _state(self, S, feat_res, batch) -> DecoderState:
-        key = (int(S), int(feat_res), int(batch), self.flat.device, bool(self.tensor_cores))
+    def _state(self, S, feat_res, batch, frames=1) -> DecoderState:
+        key = (int(S), int(feat_res), int(batch), self.flat.device, bool(self.tensor_cores), int(frames))
         st = self._states.get(key)
         if st is None:
-            st = DecoderState(S, feat_res, batch, self.flat.device, self.c_geom, self.hsize, tensor_cores=self.tensor_cores)
+            st = DecoderState(S, feat_res, batch, self.flat.device, self.c_geom, self.hsize, tensor_cores=self.tensor_cores, frames=frames)
             self._states[key] = st
         st.bn_running = self.bn_running
         st.track_running = True     # the reference never calls .eval(): BatchNorm always uses batch statistics
@@ -214,14 +214,23 @@ class POP_no_unet(nn.Module):
         """Fast path: geo_feature [1,c_geom,h,h] -> packed decoder output [S*S, 8] = (res.xyz, scale, rgb, 0), computed
         once for the whole batch (stage-1 inputs are identical across frames)."""
         st = self._state(S, geo_feature.shape[-1], batch)
-        return DecoderNet.apply(self.flat, geo_feature, st)
+        return DecoderNet.apply(self.flat, geo_feature, None, st)
+
+    def forward_packed_frames(self, geo_feature: torch.Tensor, pose_featmap: torch.Tensor, S: int) -> torch.Tensor:
+        """Stage 2 (model/network.py:55-58): pix_feature = pose_featmap [B,c,h,h] + geom convs(geo_feature), one decoder evaluation
+        per frame, BatchNorm statistics over all B*S*S positions -> packed output [B*S*S, 8]."""
+        B = int(pose_featmap.shape[0])
+        st = self._state(S, geo_feature.shape[-1], B, frames=B)
+        return DecoderNet.apply(self.flat, geo_feature, pose_featmap, st)
 
     def forward(self, pose_featmap, geom_featmap, uv_loc):
         """Reference signature (model/network.py:39): returns residuals [B,3,HW], scales [B,1,HW], shs [B,3,HW]."""
-        if pose_featmap is not None:
-            raise NotImplementedError("stage-2 pose_featmap path (SURVEY.md §8f rank 2) is not built yet")
         B = geom_featmap.shape[0]
         S = int(round(uv_loc.shape[1] ** 0.5))
+        if pose_featmap is not None:      # stage 2: per-frame inputs (the reference expands ONE geo_feature to the batch, avatar_model.py:398)
+            dec = self.forward_packed_frames(geom_featmap[:1], pose_featmap, S).reshape(B, S * S, 8)
+            t = dec.permute(0, 2, 1)                                # [B, 8, HW]
+            return t[:, 0:3], t[:, 3:4], t[:, 4:7]
         # the reference expands one geo_feature to the batch (avatar_model.py:298); identical rows -> evaluate once
         geo = geom_featmap[:1]
         dec = self.forward_packed(geo, S, B)                       # [HW, 8]

@@ -42,6 +42,7 @@ class _StepGraph:
 
 
 class Stage1Trainer:
+    """The loop body of train.py:66-97 for either training stage (the name dates from when only stage 1 existed; `AvatarTrainer` is an alias)."""
     def __init__(self, model, fused_adam: bool = True, process_group=None, use_graph=None, perceptual_loss=None):
         self.model = model
         # train.py:26,89-91: after `lpips_start_iter` epochs the reference adds lambda_lpips * LPIPS((image-0.5)*2, (gt-0.5)*2).  LPIPS is
@@ -62,8 +63,12 @@ class Stage1Trainer:
             model.training_setup()
         if fused_adam and not isinstance(model.optimizer, FusedAdam):
             # same hyper-parameters / groups / state layout as the torch.optim.Adam the reference builds (avatar_model.py:150-155)
-            model.optimizer = FusedAdam([{"params": list(model.net.parameters()), "lr": self.opt.lr_net},
-                                         {"params": [model.geo_feature], "lr": self.opt.lr_geomfeat}])
+            if getattr(model.model_parms, "train_stage", 1) == 2:
+                model.optimizer = FusedAdam([{"params": list(model.net.parameters()), "lr": self.opt.lr_net * 0.1},
+                                             {"params": list(model.pose_encoder.parameters()), "lr": self.opt.lr_net}])
+            else:
+                model.optimizer = FusedAdam([{"params": list(model.net.parameters()), "lr": self.opt.lr_net},
+                                             {"params": [model.geo_feature], "lr": self.opt.lr_geomfeat}])
             model.scheduler = torch.optim.lr_scheduler.MultiStepLR(model.optimizer, self.opt.sched_milestones, gamma=0.1)
             if prev_opt is not None and prev_opt.get("state"):
                 model.optimizer.load_state_dict(model.translate_optimizer_state(prev_opt))
@@ -74,9 +79,13 @@ class Stage1Trainer:
     def loss(self, batch, iteration: int, epoch: int = 0):
         """Forward only: returns (loss, image) exactly as train.py:70-77 forms them."""
         m, o = self.model, self.opt
-        image, points, offset_loss, geo_loss, scale_loss = m.train_stage1(batch, iteration)
         wdecay_rgl = adjust_loss_weights(o.lambda_rgl, epoch, mode="decay", start=self.epoch_start, every=20)   # train.py:60
-        loss = o.lambda_scale * scale_loss + wdecay_rgl * offset_loss + image_loss(image, batch["original_image"], o.lambda_dssim) + geo_loss
+        if getattr(m.model_parms, "train_stage", 1) == 2:                                                      # train.py:79-86
+            image, points, pose_loss, offset_loss = m.train_stage2(batch, iteration)
+            loss = wdecay_rgl * offset_loss + image_loss(image, batch["original_image"], o.lambda_dssim) + pose_loss * 10
+        else:
+            image, points, offset_loss, geo_loss, scale_loss = m.train_stage1(batch, iteration)
+            loss = o.lambda_scale * scale_loss + wdecay_rgl * offset_loss + image_loss(image, batch["original_image"], o.lambda_dssim) + geo_loss
         if epoch > o.lpips_start_iter:                   # train.py:89-91
             if self.perceptual_loss is not None:
                 gt = batch["original_image"]
@@ -99,27 +108,35 @@ class Stage1Trainer:
         if self.world == 1:
             return
         m = self.model
-        gf, gg = m.net.flat.grad, m.geo_feature.grad
-        n1, n2 = gf.numel(), gg.numel()
+        # the parameters every rank shares: stage 1 = feature net + geo_feature, stage 2 = feature net + pose encoder (avatar_model.py:148-161)
+        shared = [m.net.flat] + ([m.geo_feature] if getattr(m.model_parms, "train_stage", 1) != 2 else list(m.pose_encoder.parameters()))
+        shared = [p for p in shared if p.grad is not None]
+        sizes = [p.grad.numel() for p in shared]
+        total = sum(sizes)
+        dev = shared[0].grad.device
         bk = getattr(self, "_bucket", None)
-        if bk is None or bk.numel() != n1 + n2 + 1:
-            bk = self._bucket = torch.zeros(n1 + n2 + 1, dtype=torch.float32, device=gf.device)
-            self._skip = torch.zeros(1, dtype=torch.int32, device=gf.device)
-            self._flag_host = torch.zeros(1, dtype=torch.float32).pin_memory() if gf.is_cuda else torch.zeros(1)
-            self._flag_event = torch.cuda.Event() if gf.is_cuda else None
-        bk[:n1].copy_(gf.reshape(-1))
-        bk[n1:n1 + n2].copy_(gg.reshape(-1))
+        if bk is None or bk.numel() != total + 1:
+            bk = self._bucket = torch.zeros(total + 1, dtype=torch.float32, device=dev)
+            self._skip = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._flag_host = torch.zeros(1, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(1)
+            self._flag_event = torch.cuda.Event() if dev.type == "cuda" else None
+        off = 0
+        for p, n in zip(shared, sizes):
+            bk[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
         plan = getattr(m, "_last_plan", None)
         if plan is not None:
-            bk[n1 + n2:].copy_(plan.status_dev[1:2])
+            bk[total:].copy_(plan.status_dev[1:2])
         else:
-            bk[n1 + n2:].zero_()
+            bk[total:].zero_()
         work = dist.all_reduce(bk, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         work.wait()                                   # stream-level wait on CUDA; a host wait only with gloo (CPU tests)
-        m.net.flat.grad = bk[:n1].view_as(gf)
-        m.geo_feature.grad = bk[n1:n1 + n2].view_as(gg)
-        self._skip.copy_(bk[n1 + n2:] != 0)
-        self._flag_host.copy_(bk[n1 + n2:], non_blocking=True)
+        off = 0
+        for p, n in zip(shared, sizes):
+            p.grad = bk[off:off + n].view_as(p.grad)
+            off += n
+        self._skip.copy_(bk[total:] != 0)
+        self._flag_host.copy_(bk[total:], non_blocking=True)
         if self._flag_event is not None:
             self._flag_event.record()
 
@@ -198,7 +215,8 @@ class Stage1Trainer:
         one image size."""
         m = self.model
         img = batch.get("original_image")
-        return (self.use_graph and isinstance(m.optimizer, FusedAdam) and iteration >= 1000 and epoch <= self.opt.pose_op_start_iter
+        return (self.use_graph and isinstance(m.optimizer, FusedAdam) and getattr(m.model_parms, "train_stage", 1) != 2
+                and iteration >= 1000 and epoch <= self.opt.pose_op_start_iter
                 and not (self.perceptual_loss is not None and epoch > self.opt.lpips_start_iter)
                 and torch.is_tensor(img) and img.is_cuda and img.shape[0] <= 8 and os.environ.get("GA_RASTER_BATCHED", "1") != "0"
                 and m._uniform_frames(batch, img.shape[0]))
@@ -288,7 +306,12 @@ class Stage1Trainer:
             plan = getattr(m, "_last_plan", None)
             m.optimizer.skip_flag = self._skip if self.world > 1 else (plan.status_dev[1:2] if plan is not None else None)
         elif self.world > 1:
-            for g in (m.net.flat.grad, m.geo_feature.grad):
-                g.div_(self.world)
+            for group in m.optimizer.param_groups:
+                for p in group["params"]:
+                    if p.grad is not None:
+                        p.grad.div_(self.world)
         m.step(epoch)
         return loss
+
+
+AvatarTrainer = Stage1Trainer

@@ -152,10 +152,13 @@ int ga_smpl_backward(int32_t B, const float *pose, const float *rest_joints, con
  * Outputs per frame in the rasterizer's layout: means3D / scales3 / colors [B,N,3].  B <= 8.
  * Backward overwrites d_dec_out [num_pixels,8] (zero at invalid pixels) and d_cano2live [B,24,12].
  * ---------------------------------------------------------------------------------------------------------------- */
-int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, const float *dec_out, const int32_t *valid_index,
+int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, int64_t dec_frame_stride, const float *dec_out, const int32_t *valid_index,
                    const float *query_points, const float *query_lbs, const float *cano2live, float *means3D,
                    float *scales3, float *colors, void *stream);
-int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float scale_mul, const float *dec_out,
+/* dec_frame_stride: floats between two frames' decoder outputs — 0 in stage 1 (ONE [S*S,8] output serves every frame and the
+ * backward SUMS the frames' gradients into d_dec_out [num_pixels,8]), S*S*8 in stage 2 (per-frame outputs, model/avatar_model.py:
+ * 401-420; d_dec_out is then [B*S*S,8] and num_pixels = B*S*S). */
+int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float scale_mul, int64_t dec_frame_stride, const float *dec_out,
                     const int32_t *valid_index, const float *query_points, const float *query_lbs, const float *cano2live,
                     const float *d_means3D, const float *d_scales3, const float *d_colors, float *d_dec_out,
                     float *d_cano2live, void *stream);
@@ -179,6 +182,8 @@ typedef struct GaDecoderDesc {
     int32_t S, feat_res, batch, c_geom, hsize;
     float bn_eps, bn_momentum;
     int32_t flags;   /* GA_DECODER_TENSOR_CORES: MLP layers on tcgen05 (TF32, the reference's cuDNN numerics); 0: strict FP32 */
+    int32_t frames;  /* distinct input maps = decoder row blocks: 0 / 1 = stage 1 (one map shared by the batch), B = stage 2 (one
+                      * pose_featmap per frame, model/avatar_model.py:401-405): rows, dec_out and d_dec_out are then [frames*S*S, .] */
 } GaDecoderDesc;
 #define GA_DECODER_TENSOR_CORES 1
 typedef struct GaDecoderLayout {
@@ -192,10 +197,12 @@ typedef struct GaDecoderViews {
 } GaDecoderViews;
 int ga_decoder_layout(const GaDecoderDesc *d, GaDecoderLayout *out);
 size_t ga_decoder_workspace_bytes(const GaDecoderDesc *d);
-int ga_decoder_forward(const GaDecoderDesc *d, const float *params, const float *geo_nchw, float *bn_running,
-                       void *workspace, float *dec_out, void *stream);
+/* pose_feat_nchw [frames,64,feat_res,feat_res] (NULL in stage 1): added to the geometry convs' output before the UV up-sampling
+ * (pix_feature = pose_featmap + geom_featmap, model/network.py:58); d_pose_feat_nchw receives its gradient. */
+int ga_decoder_forward(const GaDecoderDesc *d, const float *params, const float *geo_nchw, const float *pose_feat_nchw,
+                       float *bn_running, void *workspace, float *dec_out, void *stream);
 int ga_decoder_backward(const GaDecoderDesc *d, const float *params, void *workspace, const float *dec_out,
-                        const float *d_dec_out, float *d_params, float *d_geo_nchw, void *stream);
+                        const float *d_dec_out, float *d_params, float *d_geo_nchw, float *d_pose_feat_nchw, void *stream);
 int ga_decoder_views(const GaDecoderDesc *d, void *workspace, GaDecoderViews *out);
 /* One decoder layer on the tensor cores (building block of ga_decoder_forward, exposed for unit tests):
  * Y[M,128] (+)= softplus(X * bn_a + bn_b)[M,K] W[128,K]^T + bias (bn_a == NULL: X used raw); optional per-column

@@ -80,7 +80,7 @@ def gen_smpl_A():
                         rest_joints=body.rest_joints().numpy(), body_seed=0)
 
 
-def _pop_case(name, inp, S, B, seed, hsize=128, c_geom=64):
+def _pop_case(name, inp, S, B, seed, hsize=128, c_geom=64, pose=False):
     torch.manual_seed(0)
     net = POP_no_unet(c_geom=c_geom, geom_layer_type="conv", nf=32, hsize=hsize, up_mode="upconv", use_dropout=False, uv_feat_dim=2)
     p = seeded_pop_params(seed, c_geom, hsize)
@@ -91,7 +91,9 @@ def _pop_case(name, inp, S, B, seed, hsize=128, c_geom=64):
     g = torch.Generator().manual_seed(seed + 1)
     geo = (torch.randn(1, c_geom, inp, inp, generator=g) * 0.01).requires_grad_(True)
     uv = getIdxMap_torch(torch.rand(3, S, S))            # utils/general_utils.py:188
-    res, sc, shs = net.forward(pose_featmap=None, geom_featmap=geo.expand(B, -1, -1, -1).contiguous(),
+    # stage 2 (model/avatar_model.py:401-405): a per-frame pose feature map is added to the geometry features
+    pf = (torch.randn(B, c_geom, inp, inp, generator=g) * 0.05).requires_grad_(True) if pose else None
+    res, sc, shs = net.forward(pose_featmap=pf, geom_featmap=geo.expand(B, -1, -1, -1).contiguous(),
                                uv_loc=uv[None].expand(B, -1, -1).contiguous())
     gr, gs, gc = (torch.randn(res.shape, generator=g), torch.randn(sc.shape, generator=g), torch.randn(shs.shape, generator=g))
     loss = (res * gr).sum() + (sc * gs).sum() + (shs * gc).sum()
@@ -104,6 +106,9 @@ def _pop_case(name, inp, S, B, seed, hsize=128, c_geom=64):
                geo_grad_sub=geo.grad.numpy()[:, ::4, ::max(1, inp // 8), ::max(1, inp // 8)].copy(),
                geo_grad_norm=float(geo.grad.norm()), bn1_running_mean=net.decoder.bn1.running_mean.numpy(),
                bn1_running_var=net.decoder.bn1.running_var.numpy(), inp=inp, S=S, B=B, seed=seed, hsize=hsize, c_geom=c_geom)
+    if pose:
+        out["pose_featmap"] = pf.detach().numpy()
+        out["pose_grad"] = pf.grad.numpy()
     for k in keep:
         out["grad:" + k] = grads[k][:8, :8].copy() if k.startswith("geom_proc") else grads[k]
     out["grad_norms"] = np.array([np.linalg.norm(grads[k]) for k in sorted(grads)])
@@ -115,6 +120,7 @@ def gen_pop():
     _pop_case("pop_s32_in16.npz", inp=16, S=32, B=2, seed=5)          # resample 16 -> 32, batch-identical inputs
     _pop_case("pop_s32_in32.npz", inp=32, S=32, B=1, seed=6)          # feat_res == uv_res: resample skipped (network.py:65)
     _pop_case("pop_s48_in128.npz", inp=128, S=48, B=1, seed=7)        # the real 128^2 input map, down-sampling case
+    _pop_case("pop_s32_in16_pose.npz", inp=16, S=32, B=2, seed=8, pose=True)   # stage 2: per-frame pose_featmap, BatchNorm over both frames
 
 
 def gen_losses():

@@ -253,6 +253,156 @@ def test_inference_model_caches_the_frame_invariant_decoder_output():
         n0 = list(m.net._states.values())[0].num_batches_tracked
         got = [m.render_free_stage1(b, 59400).clone() for b in batches]
         assert list(m.net._states.values())[0].num_batches_tracked == n0 + 1          # evaluated once for the three frames
-    for a, b in zip(got, ref):
-        assert torch.equal(a, b)
-    assert not torch.equal(got[0], got[1])
+    for a, b in zip(got, ref):          # the re-evaluated net differs by the summation order of its BatchNorm statistics (double atomics)
+        assert (a - b).abs().mean().item() < 1e-6 and (a - b).abs().max().item() < 1e-2
+    assert (got[0] - got[1]).abs().mean().item() > 1e-3
+
+
+# ------------------------------------------------------------------------------------------------------------- stage 2
+@pytest.mark.parametrize("mode", ["fp32", pytest.param("tf32", marks=pytest.mark.tf32)])
+def test_stage2_decoder_with_pose_featmap_matches_reference_fixture(mode):
+    """POP_no_unet.forward(pose_featmap=[B,64,h,h], ...) (model/network.py:55-58): per-frame decoder rows, BatchNorm statistics over
+    both frames — outputs, parameter / geo_feature / pose_featmap gradients of the reference module."""
+    from gaussianavatar_b200.network import POP_no_unet
+    d = np.load(os.path.join(GOLD, "pop_s32_in16_pose.npz"))
+    inp, S, B, seed = int(d["inp"]), int(d["S"]), int(d["B"]), int(d["seed"])
+    otol, gtol = (2e-4, 3e-3) if mode == "fp32" else (5e-3, 3e-2)
+    net = POP_no_unet(c_geom=64, hsize=128).to(DEV)
+    assert net.tensor_cores == (mode == "tf32")
+    net.load_state_dict(ao.seeded_pop_params(seed), strict=False)
+    g = torch.Generator().manual_seed(seed + 1)
+    geo = (torch.randn(1, 64, inp, inp, generator=g) * 0.01).to(DEV).requires_grad_(True)
+    pf = torch.tensor(d["pose_featmap"], device=DEV).requires_grad_(True)
+    _ = torch.randn(B, 64, inp, inp, generator=g)                      # keeps the generator in step with the fixture's draws
+    uv = torch.tensor(d["uv"], device=DEV)
+    res, sc, shs = net(pf, geo.expand(B, -1, -1, -1).contiguous(), uv[None].expand(B, -1, -1).contiguous())
+    assert res.shape == (B, 3, S * S) and sc.shape == (B, 1, S * S) and shs.shape == (B, 3, S * S)
+    for got, key in ((res, "res"), (sc, "scales"), (shs, "shs")):
+        ref = d[key]
+        assert np.abs(got.detach().cpu().numpy() - ref).max() < otol * max(1.0, np.abs(ref).max()), key
+    gr, gs, gc = (torch.randn(res.shape, generator=g), torch.randn(sc.shape, generator=g), torch.randn(shs.shape, generator=g))
+    ((res * gr.to(DEV)).sum() + (sc * gs.to(DEV)).sum() + (shs * gc.to(DEV)).sum()).backward()
+    grads = {k: v.cpu().numpy() for k, v in net.reference_grads().items()}
+    for k in d.files:
+        if k.startswith("grad:"):
+            n = k[5:]
+            if n in ("decoder.conv1.bias", "decoder.conv6N.bias"):
+                continue
+            got = grads[n][:8, :8] if n.startswith("geom_proc") else grads[n]
+            assert _rel(got, d[k]) < gtol, (n, _rel(got, d[k]))
+    assert _rel(pf.grad.cpu().numpy(), d["pose_grad"]) < gtol
+    assert abs(np.linalg.norm(geo.grad.cpu().numpy()) - float(d["geo_grad_norm"])) / float(d["geo_grad_norm"]) < gtol
+
+
+def test_lbs_assemble_per_frame_decoder_output():
+    """Stage 2: every frame has its own decoder rows; forward and backward against the stage-1 kernel run frame by frame."""
+    from gaussianavatar_b200 import synthetic as syn
+    from gaussianavatar_b200.ops import LbsAssemble
+    N, S, B = 900, 40, 3
+    a = syn.make_avatar_assets(N, S, seed=2)
+    g = torch.Generator().manual_seed(0)
+    dec = torch.randn(B * S * S, 8, generator=g).to(DEV).requires_grad_(True)
+    C = (torch.eye(4)[:3].reshape(1, 1, 12) + 0.05 * torch.randn(B, 24, 12, generator=g)).to(DEV).requires_grad_(True)
+    vi = torch.nonzero(a.valid_idx).reshape(-1).to(torch.int32).to(DEV)
+    q, w = a.query_points.to(DEV), a.query_lbs.to(DEV)
+    gm, gs, gc = (torch.randn(B, N, 3, generator=g).to(DEV) for _ in range(3))
+    m, s, c = LbsAssemble.apply(dec, C, vi, q, w, 0.7, True)
+    ((m * gm).sum() + (s * gs).sum() + (c * gc).sum()).backward()
+    for b in range(B):
+        db = dec.detach()[b * S * S:(b + 1) * S * S].clone().requires_grad_(True)
+        Cb = C.detach()[b:b + 1].clone().requires_grad_(True)
+        mb, sb, cb = LbsAssemble.apply(db, Cb, vi, q, w, 0.7)
+        assert torch.equal(mb[0], m[b]) and torch.equal(sb[0], s[b]) and torch.equal(cb[0], c[b])
+        ((mb * gm[b:b + 1]).sum() + (sb * gs[b:b + 1]).sum() + (cb * gc[b:b + 1]).sum()).backward()
+        assert torch.allclose(dec.grad[b * S * S:(b + 1) * S * S], db.grad, atol=1e-6)
+        assert torch.allclose(C.grad[b], Cb.grad[0], rtol=1e-4, atol=1e-5)
+
+
+def test_train_stage2_end_to_end_vs_oracle_chain(tmp_path):
+    """One whole stage-2 step (model/avatar_model.py:369-463, train.py:79-97) on a synthetic dataset folder: pose encoder -> per-frame
+    decoder -> LBS -> rasterizer -> loss -> backward, against the CPU oracle chain (reference-pinned pose encoder / POP / SMPL / losses
+    restatements + the C rasterizer oracle); then save / stage2_load round-trips the reference's `pose_encoder.pth` layout."""
+    import math
+    from dataset_fixture import write_synthetic_dataset
+    from gaussianavatar_b200.avatar_model import AvatarModel
+    from gaussianavatar_b200.config import NetworkParams, OptimizationParams
+    from gaussianavatar_b200.trainer import AvatarTrainer
+    from gaussianavatar_b200.workload import to_cuda
+    from oracle import raster_oracle as ro
+    N, S, F, side, inp = 700, 48, 4, 64, 32          # five stride-2 steps need a >= 32 input map (UnetNoCond5DS: "for posmap size=32")
+    mp = write_synthetic_dataset(str(tmp_path), N=N, S=S, num_frames=F, side=side, inp=inp, stage2=True)
+    torch.manual_seed(0)
+    m = AvatarModel(mp, NetworkParams(nf=8), OptimizationParams(), train=True)
+    with torch.no_grad():
+        sd = m.net.state_dict(); sd["decoder.conv8N.bias"] = torch.tensor([-3.5]); m.net.load_state_dict(sd, strict=False)
+    tr = AvatarTrainer(m, use_graph=False)
+    ds = m.train_dataset
+    items = [ds[1], ds[2]]
+    batch = {k: (torch.stack([torch.as_tensor(it[k]) for it in items]) if not isinstance(items[0][k], (int, float)) else [it[k] for it in items])
+             for k in items[0]}
+    batch["pose_idx"] = torch.tensor([it["pose_idx"] for it in items])
+    batch, _ = to_cuda(batch, DEV)
+    B = 2
+    with torch.backends.cudnn.flags(allow_tf32=False):       # strict-FP32 comparison: the pose encoder's cuDNN convs in fp32 like the decoder path under test
+        loss, image = tr.loss(batch, 3000, epoch=1)
+        m.zero_grad(1)
+        loss.backward()
+    # ---- oracle chain ----
+    p = {k: v.cpu().clone().requires_grad_(True) for k, v in m.net.state_dict().items() if "running" not in k and "num_batches" not in k}
+    pe = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.pose_encoder.named_parameters()}
+    geo = m.geo_feature.detach().cpu().clone().requires_grad_(True)
+    ids = batch["pose_idx"].cpu()
+    pose = m.pose.weight.detach().cpu()[ids].clone(); transl = m.transl.weight.detach().cpu()[ids].clone()
+    pf = ao.unet5ds_forward(pe, batch["inp_pos_map"].cpu().float())
+    res, sc, shs = ao.pop_forward(p, geo, S, B=B, pose_featmap=pf)
+    A = ao.smpl_joint_transforms(m._rest_joints.cpu(), pose, transl)
+    C = torch.matmul(A, m._inv_cano.cpu()[None])
+    q, w = m._query_points.cpu(), m._query_lbs.cpu()
+    o = ao.assemble_and_skin(res, sc, shs, m.valid_idx.cpu(), q[None].expand(B, -1, -1), w[None].expand(B, -1, -1), C, 3000, ramp=False)
+    cam = items[0]
+    rots = np.zeros((N, 4), np.float32); rots[:, 0] = 1
+    rs, imgs = [], []
+    for b in range(B):
+        r = ro.forward(o["means3D"][b].detach().numpy(), o["colors"][b].detach().numpy(), np.ones(N, np.float32), o["scales"][b].detach().numpy(),
+                       rots, np.ones(3, np.float32), cam["world_view_transform"].numpy(), cam["full_proj_transform"].numpy(),
+                       math.tan(cam["FovX"] / 2), math.tan(cam["FovY"] / 2), side, side)
+        rs.append(r); imgs.append(torch.tensor(r.image, dtype=torch.float32))
+    img = torch.stack(imgs).requires_grad_(True)
+    gt = batch["original_image"].cpu().float()
+    li = 0.8 * ao.l1_loss_w(img, gt) + 0.2 * (1 - ao.ssim(img, gt))
+    li.backward()
+    gm, gc, gs = [], [], []
+    for b in range(B):
+        gb = rs[b].backward(img.grad[b].numpy())
+        gm.append(torch.tensor(gb["d_means3D"], dtype=torch.float32)); gc.append(torch.tensor(gb["d_colors"], dtype=torch.float32))
+        gs.append(torch.tensor(gb["d_scales"], dtype=torch.float32))
+    reg = 10.0 * o["offset_loss"] + 10.0 * torch.mean(pf ** 2)
+    ref_loss = li.item() + reg.item()
+    torch.autograd.backward([o["means3D"], o["colors"], o["scales"], reg], [torch.stack(gm), torch.stack(gc), torch.stack(gs), torch.ones(())])
+    assert abs(loss.item() - ref_loss) < 1e-4 * max(1.0, abs(ref_loss)), (loss.item(), ref_loss)
+    assert np.abs(image.detach().cpu().numpy() - img.detach().numpy()).mean() < 1e-4
+    got = {k: v.cpu() for k, v in m.net.reference_grads().items()}
+    worst = 0.0
+    for k, v in p.items():
+        if k.endswith(".bias") and ".bn" not in k and "conv8" not in k:
+            continue
+        worst = max(worst, _rel(got[k].numpy(), v.grad.numpy()))
+    assert worst < 1e-2, worst
+    for k, v in m.pose_encoder.named_parameters():
+        assert _rel(v.grad.cpu().numpy(), pe[k].grad.numpy()) < 2e-2, k
+    # one optimizer step, then the reference's stage-2 checkpoint layout round-trips
+    m.step(1)
+    m.save(7)
+    ck = torch.load(os.path.join(m.model_path, "net/iteration_7", "pose_encoder.pth"), weights_only=False)
+    assert set(ck) == {"pose_encoder", "geo_feature", "pose", "transl", "net", "optimizer", "scheduler"}
+    assert "conv3.conv.weight" in ck["pose_encoder"] and "upconv5.up.bias" in ck["pose_encoder"]
+    before = m.pose_encoder.conv3.conv.weight.detach().clone()
+    with torch.no_grad():
+        m.pose_encoder.conv3.conv.weight.zero_()
+    mp2 = mp
+    m.model_parms.project_path = ""
+    m.stage2_load(7)
+    assert torch.equal(m.pose_encoder.conv3.conv.weight, before)
+    with torch.no_grad():
+        out = m.render_free_stage2(batch, 3000)
+    assert out.shape == (B, 3, side, side) and torch.isfinite(out).all()

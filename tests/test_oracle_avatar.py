@@ -25,7 +25,7 @@ def test_smpl_joint_transforms_match_reference_lbs():
     assert np.abs(syn.make_body(int(d["body_seed"])).rest_joints().numpy() - d["rest_joints"]).max() < 1e-6
 
 
-@pytest.mark.parametrize("name", ["pop_s32_in16.npz", "pop_s32_in32.npz", "pop_s48_in128.npz"])
+@pytest.mark.parametrize("name", ["pop_s32_in16.npz", "pop_s32_in32.npz", "pop_s48_in128.npz", "pop_s32_in16_pose.npz"])
 def test_pop_forward_backward_match_reference(name):
     d = _load(name)
     inp, S, B, seed = int(d["inp"]), int(d["S"]), int(d["B"]), int(d["seed"])
@@ -33,7 +33,10 @@ def test_pop_forward_backward_match_reference(name):
     g = torch.Generator().manual_seed(seed + 1)
     geo = (torch.randn(1, int(d["c_geom"]), inp, inp, generator=g) * 0.01).requires_grad_(True)
     assert np.abs(ao.uv_coord_map(S).numpy() - d["uv"]).max() == 0
-    res, sc, shs, stats = ao.pop_forward(p, geo, S, B=B, return_stats=True)
+    pf = torch.tensor(d["pose_featmap"]).requires_grad_(True) if "pose_featmap" in d.files else None      # stage 2 (network.py:58)
+    if pf is not None:
+        assert np.array_equal((torch.randn(B, int(d["c_geom"]), inp, inp, generator=g) * 0.05).numpy(), d["pose_featmap"])      # keeps g in step
+    res, sc, shs, stats = ao.pop_forward(p, geo, S, B=B, pose_featmap=pf, return_stats=True)
     for got, key in ((res, "res"), (sc, "scales"), (shs, "shs")):
         assert np.abs(got.detach().numpy() - d[key]).max() < 2e-5, key
     gr, gs, gc = (torch.randn(res.shape, generator=g), torch.randn(sc.shape, generator=g), torch.randn(shs.shape, generator=g))
@@ -53,6 +56,8 @@ def test_pop_forward_backward_match_reference(name):
                 continue
             assert np.linalg.norm(got - ref) / (np.linalg.norm(ref) + 1e-30) < 2e-3, n
     assert abs(float(geo.grad.norm()) - float(d["geo_grad_norm"])) / float(d["geo_grad_norm"]) < 1e-3
+    if pf is not None:
+        assert np.linalg.norm(pf.grad.numpy() - d["pose_grad"]) / np.linalg.norm(d["pose_grad"]) < 1e-3
     # running-stat update of BatchNorm (momentum 0.1, unbiased variance): pins the batch statistics themselves
     m, v = stats["bn1"]
     n = B * S * S
@@ -127,3 +132,33 @@ def test_unet5ds_oracle_matches_reference_fixture():
     assert rel(p["conv3.conv.weight"].grad.numpy(), d["d_conv3"]) < 1e-4
     assert rel(p["upconv4.up.weight"].grad.numpy(), d["d_upconv4"]) < 1e-4
     assert rel(p["upconv5.up.bias"].grad.numpy(), d["d_bias"]) < 1e-4
+
+
+def test_product_pose_encoder_matches_reference_fixture():
+    """gaussianavatar_b200.pose_encoder.UnetNoCond5DS (the product module; torch ops, runs on any device) against the outputs / gradients /
+    running statistics of the reference's UnetNoCond5DS, and its state_dict carries the reference's names."""
+    from gaussianavatar_b200.pose_encoder import UnetNoCond5DS
+    d = np.load(os.path.join(GOLD, "unet5ds_nf8_s32.npz"))
+    nf, cin, cout, side, B, seed = (int(d[k]) for k in ("nf", "cin", "cout", "side", "B", "seed"))
+    net = UnetNoCond5DS(input_nc=cin, output_nc=cout, nf=nf, up_mode="upconv", use_dropout=False)
+    ref_names = set(ao.unet5ds_param_shapes(cin, cout, nf))
+    assert ref_names == {k for k, _ in net.named_parameters()}
+    sd = net.state_dict()
+    for k in ("conv2.bn.running_mean", "conv4.bn.running_var", "upconv1.bn.num_batches_tracked", "upconv4.bn.running_mean"):
+        assert k in sd
+    assert not any(k.startswith(("conv1.bn", "conv5.bn", "upconv5.bn")) for k in sd)
+    missing, unexpected = net.load_state_dict(ao.seeded_unet_params(seed, cin, cout, nf), strict=False)
+    assert not unexpected and all("running" in k or "num_batches" in k for k in missing)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, cin, side, side, generator=g).requires_grad_(True)
+    gout = torch.randn(B, cout, side, side, generator=g)
+    y = net(x)
+    (y * gout).sum().backward()
+    assert np.abs(y.detach().numpy() - d["y"]).max() < 2e-5
+    assert np.abs(x.grad.numpy() - d["dx"]).max() < 2e-4 * max(1.0, np.abs(d["dx"]).max())
+    grads = dict(net.named_parameters())
+    for name, key in (("conv3.conv.weight", "d_conv3"), ("upconv4.up.weight", "d_upconv4"), ("upconv5.up.bias", "d_bias")):
+        ref = d[key]
+        assert np.abs(grads[name].grad.numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), name
+    assert np.abs(net.conv2.bn.running_mean.numpy() - d["bn2_running_mean"]).max() < 1e-6
+    assert int(net.conv2.bn.num_batches_tracked) == 1

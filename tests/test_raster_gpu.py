@@ -249,3 +249,25 @@ def test_batched_overflow_is_flagged_not_overrun_and_recovers():
     for b, sc in enumerate(scs):
         o = ro.forward(**oracle_args(sc), precision="f32")
         assert np.abs(img[b].cpu().numpy().astype(np.float64) - o.image).mean() <= 1e-4
+
+
+@pytest.mark.parametrize("kind", ["pairs", "pile"])
+def test_equal_depths_keep_upstream_tie_order(kind):
+    """Equal depth bits inside a tile: upstream's stable key sort leaves them in Gaussian-index order.  'pairs': every Gaussian has an
+    exact duplicate; 'pile': hundreds share one position (one depth bin overflows -> the sort kernel's bitonic fallback)."""
+    from oracle import raster_oracle as ro
+    sc = random_scene(P=2400, H=96, W=96, seed=51, scale_mean=0.02, aniso=False)
+    if kind == "pairs":
+        for k in ("means3D", "scales"):
+            sc[k][1200:] = sc[k][:1200]
+    else:
+        sc["means3D"][300:1000] = sc["means3D"][299]
+        sc["scales"][300:1000] = sc["scales"][299]
+    color, radii, ctx, rs, _ = _run_cuda(sc)
+    v = ctx.views()
+    o = ro.forward(**oracle_args(sc), precision="f32")
+    k = o.get("keys")
+    assert (k[1:] == k[:-1]).sum() > (500 if kind == "pairs" else 300)          # the case really has ties
+    np.testing.assert_array_equal(v["keys_sorted"].numpy().view(np.uint64), k)
+    np.testing.assert_array_equal(v["vals_sorted"].numpy().view(np.uint32), o.get("vals"))
+    assert np.abs(color.cpu().numpy().astype(np.float64) - o.image).mean() <= 1e-4
