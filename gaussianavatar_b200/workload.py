@@ -89,8 +89,13 @@ class Stage1Workload:
 
     def device_batch(self, ids):
         """Batch dict (scene/dataset_mono.py:238-255 keys) with inputs already resident in HBM."""
-        # pinned staging + asynchronous copy: a pageable `torch.tensor(ids, device=...)` would make the host wait for the whole stream
-        idx = torch.tensor(ids).pin_memory().to(self.device, non_blocking=True)
+        # the index tensors live on the device (one per distinct id tuple): building one per step from host data costs either a
+        # stream-synchronising pageable copy or a pinned allocation, both of which stall the enqueueing thread
+        cache = self.__dict__.setdefault("_idx_cache", {})
+        key = tuple(ids)
+        if key not in cache:
+            cache[key] = torch.tensor(ids, device=self.device)
+        idx = cache[key]
         return dict(pose_idx=idx, original_image=self.gt_dev[idx], **self.camera_fields(len(ids)))
 
     def host_batch(self, ids):
