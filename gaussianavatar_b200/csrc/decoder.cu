@@ -114,6 +114,7 @@ Workspace carve_ws(void *buf, int S, int Hf, int frames)
 // [C, P] <-> [P, C] with C = 64 (tile transpose through shared memory)
 __global__ void __launch_bounds__(256) chw_to_hwc_kernel(const float *__restrict__ in, float *__restrict__ out, int P)
 {
+    pdl_wait();
     __shared__ float t[64][65];
     const int p0 = blockIdx.x * 64;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(256) chw_to_hwc_kernel(const float *__restrict
 }
 __global__ void __launch_bounds__(256) hwc_to_chw_kernel(const float *__restrict__ in, float *__restrict__ out, int P)
 {
+    pdl_wait();
     __shared__ float t[64][65];
     const int p0 = blockIdx.x * 64;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(256) hwc_to_chw_kernel(const float *__restrict
 // out[p][c] = in_chw[c][p] + base[p][c]: the per-frame decoder input map of stage 2, pose_featmap + geom_featmap (model/network.py:58)
 __global__ void __launch_bounds__(256) chw_to_hwc_add_kernel(const float *__restrict__ in, const float *__restrict__ base, float *__restrict__ out, int P)
 {
+    pdl_wait();
     __shared__ float t[64][65];
     const int p0 = blockIdx.x * 64;
     in += (size_t)blockIdx.y * 64 * P; out += (size_t)blockIdx.y * 64 * P;
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(256) chw_to_hwc_add_kernel(const float *__rest
 // out[i] = sum_f in[f][i]
 __global__ void __launch_bounds__(256) sum_frames_kernel(const float4 *__restrict__ in, float4 *__restrict__ out, size_t n4, int frames)
 {
+    pdl_wait();
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n4) return;
     float4 a = in[i];
@@ -189,6 +193,7 @@ __device__ __forceinline__ Taps make_taps(int i, int j, int S, int Hf)
 __global__ void __launch_bounds__(256)
 sample_feat_fwd_kernel(int S, int Hf, int frames, size_t frame_stride, const float *__restrict__ F, float *__restrict__ feat)
 {
+    pdl_wait();
     const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
     const size_t m = gid >> 4;
     const int q = (int)(gid & 15);
@@ -224,6 +229,7 @@ sample_feat_fwd_kernel(int S, int Hf, int frames, size_t frame_stride, const flo
 __global__ void __launch_bounds__(256)
 sample_feat_bwd_kernel(int S, int Hf, int frames, size_t frame_stride, const float *__restrict__ d_feat, float *__restrict__ dF)
 {
+    pdl_wait();
     const size_t gid = (size_t)blockIdx.x * 256 + threadIdx.x;
     const size_t m = gid >> 4;
     const int q = (int)(gid & 15);
@@ -255,6 +261,7 @@ __global__ void bn_finalize_fwd_kernel(int C, double count, double count_running
                                        float *__restrict__ mean, float *__restrict__ rstd, float *__restrict__ a,
                                        float *__restrict__ b, float *__restrict__ run_mean, float *__restrict__ run_var)
 {
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double mu = sum[c] / count;
@@ -275,6 +282,7 @@ __global__ void bn_finalize_bwd_kernel(int C, double count, const double *__rest
                                        float *__restrict__ ga, float *__restrict__ m1, float *__restrict__ m2,
                                        float *__restrict__ d_gamma, float *__restrict__ d_beta)
 {
+    pdl_wait();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     ga[c] = gamma[c] * rstd[c];
@@ -323,6 +331,7 @@ __global__ void __launch_bounds__(256, GA_HEADS_MINB)
 heads_fwd_kernel(size_t M, const float *__restrict__ Y7 /*[M,384]*/, const float *__restrict__ a7, const float *__restrict__ b7,
                  const float *__restrict__ W8 /*[8,128]*/, const float *__restrict__ b8, float *__restrict__ dec /*[M,8]*/)
 {
+    pdl_wait();
     const int lane = threadIdx.x & 31, c = lane * 4;
     float4 A[3], B[3], Wv[7];
 #pragma unroll
@@ -375,6 +384,7 @@ heads_bwd_kernel(size_t M, const float *__restrict__ Y7, const float *__restrict
                  const float *__restrict__ dec, const float *__restrict__ d_dec, float *__restrict__ dZ7,
                  double *__restrict__ s1, double *__restrict__ s2, float *__restrict__ dW8, float *__restrict__ db8)
 {
+    pdl_wait();
     constexpr int NOUT = (HEAD == 1) ? 1 : 3;
     constexpr int ROW0 = (HEAD == 0) ? 0 : (HEAD == 1 ? 3 : 4);
     __shared__ float sacc[NOUT + 2][kH];
@@ -539,7 +549,7 @@ int launch_gemm(const char *name, const AL &A, const BL &B, const EP &E, int Mg,
     dim3 grid(cdiv(Mg, BM), cdiv(Ng, BN), splits);
     {
         ProfScope _ps(name, st);
-        gemm_kernel<BM, BN, AL, BL, EP><<<grid, kGemmThreads, 0, st>>>(A, B, E, Kg, kps);
+        launch_k(gemm_kernel<BM, BN, AL, BL, EP>, grid, kGemmThreads, 0, st, A, B, E, Kg, kps);
     }
     GA_CHECK_LAUNCH(name);
     return GA_OK;
@@ -603,7 +613,7 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
 
     {
         ProfScope _ps("chw_to_hwc_kernel", st);
-        chw_to_hwc_kernel<<<cdiv(P, 64), 256, 0, st>>>(geo_nchw, w.F[0], P);
+        launch_k(chw_to_hwc_kernel, cdiv(P, 64), 256, 0, st, geo_nchw, w.F[0], P);
     }
     GA_CHECK_LAUNCH("chw_to_hwc_kernel");
     if (d->flags & GA_DECODER_TENSOR_CORES) {
@@ -627,13 +637,13 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
     if (pose_feat_nchw) {          // stage 2: pix_feature = pose_featmap + geom_featmap (model/network.py:58), one map per frame
         ProfScope _ps("chw_to_hwc_add_kernel", st);
         float *Fp = frames > 1 ? w.Fp : w.F[3];
-        chw_to_hwc_add_kernel<<<dim3(cdiv(P, 64), frames), 256, 0, st>>>(pose_feat_nchw, w.F[3], Fp, P);
+        launch_k(chw_to_hwc_add_kernel, dim3(cdiv(P, 64), frames), 256, 0, st, pose_feat_nchw, w.F[3], Fp, P);
         Fsrc = Fp; fstride = frames > 1 ? (size_t)P * kCg : 0;
     }
     if (pose_feat_nchw) GA_CHECK_LAUNCH("chw_to_hwc_add_kernel");
     {
         ProfScope _ps("sample_feat_fwd_kernel", st);
-        sample_feat_fwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, frames, fstride, Fsrc, w.feat);
+        launch_k(sample_feat_fwd_kernel, cdiv((long long)M * 16, 256), 256, 0, st, S, Hf, frames, fstride, Fsrc, w.feat);
     }
     GA_CHECK_LAUNCH("sample_feat_fwd_kernel");
     GA_CHECK_CUDA(cudaMemsetAsync(w.stat, 0, sizeof(double) * 2 * kBnCh, st));
@@ -643,7 +653,7 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
         const int o = kBnOff[l];
         {
             ProfScope _ps("bn_finalize_fwd_kernel", st);
-            bn_finalize_fwd_kernel<<<cdiv(C, 128), 128, 0, st>>>(C, (double)M, (double)S * S * d->batch, d->bn_eps, d->bn_momentum, sum + o, sumsq + o,
+            launch_k(bn_finalize_fwd_kernel, cdiv(C, 128), 128, 0, st, C, (double)M, (double)S * S * d->batch, d->bn_eps, d->bn_momentum, sum + o, sumsq + o,
                                                                  params + L.gamma[l] , params + L.beta[l], cf.mean + o, cf.rstd + o, cf.a + o, cf.b + o,
                                                                  bn_running ? bn_running + o : nullptr, bn_running ? bn_running + kBnCh + o : nullptr);
         }
@@ -714,9 +724,9 @@ extern "C" int ga_decoder_forward(const GaDecoderDesc *d, const float *params, c
     {
         ProfScope _ps("heads_fwd_kernel", st);
         if (d->flags & GA_DECODER_TENSOR_CORES)
-            heads_fwd_kernel<true><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
+            launch_k(heads_fwd_kernel<true>, kHeadsGrid, 256, 0, st, (size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
         else
-            heads_fwd_kernel<false><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
+            launch_k(heads_fwd_kernel<false>, kHeadsGrid, 256, 0, st, (size_t)M, w.Y7, cf.a + kBnOff[6], cf.b + kBnOff[6], params + L.w8, params + L.b8, dec_out);
     }
     GA_CHECK_LAUNCH("heads_fwd_kernel");
     return GA_OK;
@@ -745,7 +755,7 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         const int o = kBnOff[l];
         {
             ProfScope _ps("bn_finalize_bwd_kernel", st);
-            bn_finalize_bwd_kernel<<<cdiv(C, 128), 128, 0, st>>>(C, (double)M, s1 + o, s2 + o, params + L.gamma[l], cf.rstd + o, cf.ga + o, cf.m1 + o,
+            launch_k(bn_finalize_bwd_kernel, cdiv(C, 128), 128, 0, st, C, (double)M, s1 + o, s2 + o, params + L.gamma[l], cf.rstd + o, cf.ga + o, cf.m1 + o,
                                                                  cf.m2 + o, d_params + L.gamma[l], d_params + L.beta[l]);
         }
         GA_CHECK_LAUNCH("bn_finalize_bwd_kernel");
@@ -759,30 +769,30 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
         {
             ProfScope _ps("heads_bwd_kernel<0>", st);
             if (d->flags & GA_DECODER_TENSOR_CORES)
-                heads_bwd_kernel<0, true><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                launch_k(heads_bwd_kernel<0, true>, kHeadsGrid, 256, 0, st, (size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                    dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
             else
-                heads_bwd_kernel<0, false><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                launch_k(heads_bwd_kernel<0, false>, kHeadsGrid, 256, 0, st, (size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                     dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
         }
         GA_CHECK_LAUNCH("heads_bwd_kernel<0>");
         {
             ProfScope _ps("heads_bwd_kernel<1>", st);
             if (d->flags & GA_DECODER_TENSOR_CORES)
-                heads_bwd_kernel<1, true><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                launch_k(heads_bwd_kernel<1, true>, kHeadsGrid, 256, 0, st, (size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                    dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
             else
-                heads_bwd_kernel<1, false><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                launch_k(heads_bwd_kernel<1, false>, kHeadsGrid, 256, 0, st, (size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                     dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
         }
         GA_CHECK_LAUNCH("heads_bwd_kernel<1>");
         {
             ProfScope _ps("heads_bwd_kernel<2>", st);
             if (d->flags & GA_DECODER_TENSOR_CORES)
-                heads_bwd_kernel<2, true><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                launch_k(heads_bwd_kernel<2, true>, kHeadsGrid, 256, 0, st, (size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                    dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
             else
-                heads_bwd_kernel<2, false><<<kHeadsGrid, 256, 0, st>>>((size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
+                launch_k(heads_bwd_kernel<2, false>, kHeadsGrid, 256, 0, st, (size_t)M, w.Y7, cf.a + o7, cf.b + o7, cf.mean + o7, cf.rstd + o7, params + L.w8,
                                                                     dec_out, d_dec_out, w.dZ7, s1 + o7, s2 + o7, d_params + L.w8, d_params + L.b8);
         }
         GA_CHECK_LAUNCH("heads_bwd_kernel<2>");
@@ -902,19 +912,19 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
     GA_CHECK_CUDA(cudaMemsetAsync(dsink, 0, sizeof(float) * (size_t)frames * P * kCg, st));
     {
         ProfScope _ps("sample_feat_bwd_kernel", st);
-        sample_feat_bwd_kernel<<<cdiv((long long)M * 16, 256), 256, 0, st>>>(S, Hf, frames, frames > 1 ? (size_t)P * kCg : 0, w.d_feat, dsink);
+        launch_k(sample_feat_bwd_kernel, cdiv((long long)M * 16, 256), 256, 0, st, S, Hf, frames, frames > 1 ? (size_t)P * kCg : 0, w.d_feat, dsink);
     }
     GA_CHECK_LAUNCH("sample_feat_bwd_kernel");
     if (d_pose_feat_nchw) {        // d pose_featmap[f] = d pix[f] (NCHW); d geom_featmap = sum over the frames
         for (int f = 0; f < frames; ++f) {
             ProfScope _ps("hwc_to_chw_kernel", st);
-            hwc_to_chw_kernel<<<cdiv(P, 64), 256, 0, st>>>(dsink + (size_t)f * P * kCg, d_pose_feat_nchw + (size_t)f * P * kCg, P);
+            launch_k(hwc_to_chw_kernel, cdiv(P, 64), 256, 0, st, dsink + (size_t)f * P * kCg, d_pose_feat_nchw + (size_t)f * P * kCg, P);
             GA_CHECK_LAUNCH("hwc_to_chw_kernel");
         }
     }
     if (frames > 1) {
         ProfScope _ps("sum_frames_kernel", st);
-        sum_frames_kernel<<<cdiv((long long)P * kCg / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(w.dFp), reinterpret_cast<float4 *>(w.dF[0]),
+        launch_k(sum_frames_kernel, cdiv((long long)P * kCg / 4, 256), 256, 0, st, reinterpret_cast<const float4 *>(w.dFp), reinterpret_cast<float4 *>(w.dF[0]),
                                                                             (size_t)P * kCg / 4, frames);
     }
     if (frames > 1) GA_CHECK_LAUNCH("sum_frames_kernel");
@@ -946,7 +956,7 @@ extern "C" int ga_decoder_backward(const GaDecoderDesc *d, const float *params, 
     }
     {
         ProfScope _ps("hwc_to_chw_kernel", st);
-        hwc_to_chw_kernel<<<cdiv(P, 64), 256, 0, st>>>(dcur, d_geo_nchw, P);
+        launch_k(hwc_to_chw_kernel, cdiv(P, 64), 256, 0, st, dcur, d_geo_nchw, P);
     }
     GA_CHECK_LAUNCH("hwc_to_chw_kernel");
     return GA_OK;

@@ -72,6 +72,7 @@ lbs_kernel(int N, int B, float scale_mul, long long dec_stride /*floats between 
            const float *__restrict__ d_means, const float *__restrict__ d_scales3, const float *__restrict__ d_colors,
            float *__restrict__ d_dec /*[S*S,8], pre-zeroed*/, float *__restrict__ dC /*[B,24,12], pre-zeroed*/)
 {
+    pdl_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LbsSmem &sm = *reinterpret_cast<LbsSmem *>(smem_raw);
     const int tid = threadIdx.x;
@@ -236,7 +237,7 @@ extern "C" int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, int64_t dec
         GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
         attr_set = true;
     }
-    { ProfScope _ps("lbs_kernel<fwd>", static_cast<cudaStream_t>(stream_)); lbs_kernel<false><<<launch_cfg(N), kTileN, sizeof(LbsSmem), static_cast<cudaStream_t>(stream_)>>>(
+    { ProfScope _ps("lbs_kernel<fwd>", static_cast<cudaStream_t>(stream_)); launch_k(lbs_kernel<false>, launch_cfg(N), kTileN, sizeof(LbsSmem), static_cast<cudaStream_t>(stream_), 
         N, B, scale_mul, (long long)dec_frame_stride, dec_out, valid_index, query_points, query_lbs, cano2live, means3D, scales3, colors, nullptr, nullptr,
         nullptr, nullptr, nullptr); }
     GA_CHECK_LAUNCH("lbs_kernel<fwd>");
@@ -260,7 +261,7 @@ extern "C" int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float s
         GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
         attr_set = true;
     }
-    { ProfScope _ps("lbs_kernel<bwd>", stream); lbs_kernel<true><<<launch_cfg(N), kTileN, sizeof(LbsSmem), stream>>>(N, B, scale_mul, (long long)dec_frame_stride, dec_out, valid_index, query_points,
+    { ProfScope _ps("lbs_kernel<bwd>", stream); launch_k(lbs_kernel<true>, launch_cfg(N), kTileN, sizeof(LbsSmem), stream, N, B, scale_mul, (long long)dec_frame_stride, dec_out, valid_index, query_points,
                                                                         query_lbs, cano2live, nullptr, nullptr, nullptr,
                                                                         d_means3D, d_scales3, d_colors, d_dec_out, d_cano2live); }
     GA_CHECK_LAUNCH("lbs_kernel<bwd>");

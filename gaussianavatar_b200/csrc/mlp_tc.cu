@@ -101,6 +101,7 @@ tc_fwd_kernel(const TcFwdParams p)
         fence_barrier_init();
     }
     if (warp == kFwdMmaWarp) tmem_alloc(&sm.tmem_base, kTmemCols);
+    pdl_wait();            // everything above touches only this CTA's shared / tensor memory: it overlaps the previous kernel's tail
     // weights -> shared, K-major, 128-byte swizzle
     for (int i = tid; i < kBN * (p.K / 4); i += kTcThreads) {
         const int n = i / (p.K / 4), q = i % (p.K / 4);
@@ -299,7 +300,7 @@ int launch_tc_fwd(const float *X, int ldx, int K, const float *a, const float *b
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     {
         ProfScope _ps("mlp_tc_fwd", st);
-        tc_fwd_kernel<<<grid, kTcThreads, sizeof(TcFwdSmem) + 1024, st>>>(p);
+        launch_k(tc_fwd_kernel, grid, kTcThreads, sizeof(TcFwdSmem) + 1024, st, p);
     }
     GA_CHECK_LAUNCH("tc_fwd_kernel");
     return GA_OK;
@@ -394,6 +395,7 @@ tc_bwd_kernel(const TcBwdParams p)
         fence_barrier_init();
     }
     if (warp == kBwdMmaWarp) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
+    pdl_wait();            // barrier init and TMEM allocation above overlap the previous kernel's tail
     // W^T -> shared (K-major over the OUTPUT channel): element (in, out) <- W[out][in]
     const int kq = p.kin >> 2;
     for (int i = tid; i < 128 * kq; i += kBwdThreads) {
@@ -671,7 +673,7 @@ int launch_tc_bwd(const float *dZ, const float *Y, int ldg, const float *ga, con
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     {
         ProfScope _ps("mlp_tc_bwd", st);
-        tc_bwd_kernel<<<grid, kBwdThreads, sizeof(TcBwdSmem) + 1024, st>>>(p);
+        launch_k(tc_bwd_kernel, grid, kBwdThreads, sizeof(TcBwdSmem) + 1024, st, p);
     }
     GA_CHECK_LAUNCH("tc_bwd_kernel");
     return GA_OK;

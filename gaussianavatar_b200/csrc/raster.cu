@@ -333,6 +333,7 @@ preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, CamSrc cam, float mod
                       uint32_t *__restrict__ tiles, ushort4 *__restrict__ rect, int32_t *__restrict__ radii,
                       uint32_t *__restrict__ tile_count)
 {
+    pdl_wait();
     const int b = blockIdx.y;
     __shared__ float view[16], proj[16];
     if (threadIdx.x < 16) view[threadIdx.x] = cam.view[(size_t)b * cam.stride + threadIdx.x];
@@ -377,6 +378,7 @@ tile_scan_kernel(int n, int T, long long capacity, const uint32_t *__restrict__ 
                  uint32_t *__restrict__ cursor, uint32_t *__restrict__ seg_start, uint32_t *__restrict__ order,
                  int32_t *__restrict__ status)
 {
+    pdl_wait();
     using Scan = cub::BlockScan<unsigned long long, 1024>;
     __shared__ typename Scan::TempStorage tmp;
     __shared__ unsigned long long carry_c, carry_s;
@@ -443,6 +445,7 @@ bucket_scatter_kernel(int P, int gx, int T, long long capacity, const float *__r
                       const uint32_t *__restrict__ tiles, const ushort4 *__restrict__ rect, uint32_t *__restrict__ cursor,
                       uint64_t *__restrict__ bucket)
 {
+    pdl_wait();
     const int b = blockIdx.y;
     const int il = blockIdx.x * blockDim.x + threadIdx.x;
     ushort4 rc = make_ushort4(0, 0, 0, 0);
@@ -534,6 +537,7 @@ tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const
                  float4 *__restrict__ recB, float4 *__restrict__ recC, uint32_t *__restrict__ seg_tile,
                  uint32_t *__restrict__ tile_maxc)
 {
+    pdl_wait();
     extern __shared__ uint64_t s_keys[];
     using BinScan = cub::BlockScan<uint32_t, kSortThreads>;
     __shared__ typename BinScan::TempStorage s_scan;
@@ -717,6 +721,7 @@ render_fwd_kernel(int H, int W, int gx, int T_tiles, const uint32_t *__restrict_
                   uint32_t *__restrict__ n_contrib, float4 *__restrict__ final_state, uint32_t *__restrict__ tile_maxc,
                   float *__restrict__ out)
 {
+    pdl_wait();
     __shared__ float4 s_a[kBlock / 32][32], s_b[kBlock / 32][32], s_c[kBlock / 32][32];
 
     const int blk = (int)order[blockIdx.x];           // longest tile lists first
@@ -834,6 +839,7 @@ render_bwd_kernel(int H, int W, int gx, int T_tiles, int P, const int32_t *__res
                   const uint32_t *__restrict__ n_contrib, const float *__restrict__ dL_dout,
                   float2 *__restrict__ d_mean2D, float4 *__restrict__ d_conic_op, float *__restrict__ d_colors)
 {
+    pdl_wait();
     __shared__ float4 s_a[kSeg], s_b[kSeg], s_c[kSeg];
     __shared__ float s_acc[9][kSeg];
 
@@ -971,6 +977,7 @@ preprocess_bwd_kernel(int P, int H, int W, CamSrc cam, float mod, const float *_
                       float *__restrict__ d_means3D, float *__restrict__ d_scales, float *__restrict__ d_rots,
                       float *__restrict__ d_opac, float *__restrict__ d_means2D_out)
 {
+    pdl_wait();
     const int fb = blockIdx.y;
     __shared__ float view[16], proj[16];
     if (threadIdx.x < 16) view[threadIdx.x] = cam.view[(size_t)fb * cam.stride + threadIdx.x];
@@ -1122,14 +1129,14 @@ int launch_preprocess(const Dims &d, const CamSrc &cam, const FwdArgs &a, long l
     GA_CHECK_CUDA(cudaMemsetAsync(iv.count, 0, sizeof(uint32_t) * BT, stream));
     if (d.P > 0) {
         ProfScope _ps("preprocess_fwd_kernel", stream);
-        preprocess_fwd_kernel<true><<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.H, d.W, d.gx, d.gy, cam, a.mod, a.means3D, a.scales,
+        launch_k(preprocess_fwd_kernel<true>, dim3(cdiv(d.P, 256), d.B), 256, 0, stream, d.P, d.H, d.W, d.gx, d.gy, cam, a.mod, a.means3D, a.scales,
                                                                                   a.rotations, a.rot_stride, a.opacities, a.opac_stride, g.depth,
                                                                                   g.xy, g.conic_o, g.cov3d, g.tiles, g.rect, radii, iv.count);
         GA_CHECK_LAUNCH("preprocess_fwd_kernel");
     }
     {
         ProfScope _ps("tile_scan_kernel", stream);
-        tile_scan_kernel<<<1, 1024, 0, stream>>>((int)BT, d.T, capacity, iv.count, iv.ranges, iv.cursor, iv.seg_start, iv.order, iv.status);
+        launch_k(tile_scan_kernel, 1, 1024, 0, stream, (int)BT, d.T, capacity, iv.count, iv.ranges, iv.cursor, iv.seg_start, iv.order, iv.status);
     }
     GA_CHECK_LAUNCH("tile_scan_kernel");
     return GA_OK;
@@ -1148,21 +1155,21 @@ int launch_binning_and_render(const Dims &d, const FwdArgs &a, long long capacit
     if (d.P > 0) {
         {
             ProfScope _ps("bucket_scatter_kernel", stream);
-            bucket_scatter_kernel<true><<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.gx, d.T, capacity, g.depth, g.tiles, g.rect, iv.cursor,
+            launch_k(bucket_scatter_kernel<true>, dim3(cdiv(d.P, 256), d.B), 256, 0, stream, d.P, d.gx, d.T, capacity, g.depth, g.tiles, g.rect, iv.cursor,
                                                                                       bv.bucket);
         }
         GA_CHECK_LAUNCH("bucket_scatter_kernel");
     }
     {
         ProfScope _ps("tile_sort_kernel", stream);
-        tile_sort_kernel<<<min(BT, 3 * num_sms()), kSortThreads, kSortMax * sizeof(uint64_t), stream>>>(
+        launch_k(tile_sort_kernel, min(BT, 3 * num_sms()), kSortThreads, kSortMax * sizeof(uint64_t), stream, 
             d.P, d.T, BT, iv.status, iv.order, iv.ranges, iv.seg_start, bv.bucket, g.xy, g.conic_o, a.colors, bv.point_list, bv.recA, bv.recB,
             bv.recC, bv.seg_tile, iv.tile_maxc);
     }
     GA_CHECK_LAUNCH("tile_sort_kernel");
     {
         ProfScope _ps("render_fwd_kernel", stream);
-        render_fwd_kernel<<<BT, kBlock, 0, stream>>>(d.H, d.W, d.gx, d.T, iv.order, iv.ranges, iv.seg_start, bv.recA, bv.recB, bv.recC, a.bg, bv.ckpt,
+        launch_k(render_fwd_kernel, BT, kBlock, 0, stream, d.H, d.W, d.gx, d.T, iv.order, iv.ranges, iv.seg_start, bv.recA, bv.recB, bv.recC, a.bg, bv.ckpt,
                                                     iv.final_T, iv.n_contrib, iv.final_state, iv.tile_maxc, out_color);
     }
     GA_CHECK_LAUNCH("render_fwd_kernel");
@@ -1195,18 +1202,18 @@ int launch_backward(const Dims &d, const CamSrc &cam, const BwdArgs &a, const in
         ProfScope _ps("render_bwd_kernel", stream);
         const int grid = (int)bv.max_segments;
         if (a.d_opacities)
-            render_bwd_kernel<true><<<grid, kBlock, 0, stream>>>(d.H, d.W, d.gx, d.T, d.P, iv.status, bv.seg_tile, iv.seg_start, iv.ranges,
+            launch_k(render_bwd_kernel<true>, grid, kBlock, 0, stream, d.H, d.W, d.gx, d.T, d.P, iv.status, bv.seg_tile, iv.seg_start, iv.ranges,
                                                                  iv.tile_maxc, bv.recA, bv.recB, bv.recC, bv.ckpt, a.bg, iv.final_state,
                                                                  iv.n_contrib, a.dL_dout, d_mean2D, d_conic_op, a.d_colors);
         else
-            render_bwd_kernel<false><<<grid, kBlock, 0, stream>>>(d.H, d.W, d.gx, d.T, d.P, iv.status, bv.seg_tile, iv.seg_start, iv.ranges,
+            launch_k(render_bwd_kernel<false>, grid, kBlock, 0, stream, d.H, d.W, d.gx, d.T, d.P, iv.status, bv.seg_tile, iv.seg_start, iv.ranges,
                                                                   iv.tile_maxc, bv.recA, bv.recB, bv.recC, bv.ckpt, a.bg, iv.final_state,
                                                                   iv.n_contrib, a.dL_dout, d_mean2D, d_conic_op, a.d_colors);
     }
     GA_CHECK_LAUNCH("render_bwd_kernel");
     {
         ProfScope _ps("preprocess_bwd_kernel", stream);
-        preprocess_bwd_kernel<<<dim3(cdiv(d.P, 256), d.B), 256, 0, stream>>>(d.P, d.H, d.W, cam, a.mod, a.means3D, a.scales, a.rotations,
+        launch_k(preprocess_bwd_kernel, dim3(cdiv(d.P, 256), d.B), 256, 0, stream, d.P, d.H, d.W, cam, a.mod, a.means3D, a.scales, a.rotations,
                                                                             a.rot_stride, radii, g.cov3d, d_mean2D, d_conic_op, a.d_means3D,
                                                                             a.d_scales, a.d_rotations, a.d_opacities, a.d_means2D);
     }
@@ -1312,7 +1319,11 @@ extern "C" const int32_t *ga_rasterb_status(int32_t B, int32_t H, int32_t W, con
 
 namespace ga {
 namespace {
-__global__ void stamp_serial_kernel(int32_t *status, const int32_t *serial) { status[kStatusInts - 1] = *serial; }
+__global__ void stamp_serial_kernel(int32_t *status, const int32_t *serial)
+{
+    pdl_wait();
+    status[kStatusInts - 1] = *serial;
+}
 }  // namespace
 }  // namespace ga
 
@@ -1325,7 +1336,7 @@ extern "C" int ga_rasterb_status_to_host(int32_t B, int32_t H, int32_t W, void *
     GA_REQUIRE(img && serial_dev && host16, "NULL pointer argument");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     int32_t *status = carve_img(img, make_dims(B, 0, H, W)).status;
-    stamp_serial_kernel<<<1, 1, 0, stream>>>(status, serial_dev);
+    launch_k(stamp_serial_kernel, 1, 1, 0, stream, status, serial_dev);
     GA_CHECK_LAUNCH("stamp_serial_kernel");
     GA_CHECK_CUDA(cudaMemcpyAsync(host16, status, sizeof(int32_t) * kStatusInts, cudaMemcpyDeviceToHost, stream));
     return GA_OK;

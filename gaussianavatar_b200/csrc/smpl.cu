@@ -51,6 +51,7 @@ smpl_fwd_kernel(int B, const float *__restrict__ pose, const float *__restrict__
                 const float *__restrict__ inv_cano /*[24,4,4]*/, float *__restrict__ C /*[B,24,12]*/,
                 float *__restrict__ G_out /*[B,24,12] saved for backward*/)
 {
+    pdl_wait();
     __shared__ float sL[24][12], sG[24][12];
     const int b = blockIdx.x, j = threadIdx.x;
     if (b >= B) return;
@@ -104,6 +105,7 @@ smpl_bwd_kernel(int B, const float *__restrict__ pose, const float *__restrict__
                 const float *__restrict__ G_saved, const float *__restrict__ dC /*[B,24,12]*/,
                 float *__restrict__ d_pose /*[B,72]*/, float *__restrict__ d_transl /*[B,3]*/)
 {
+    pdl_wait();
     __shared__ float sL[24][12], sG[24][12], sdG[24][12], sdL[24][9];
     const int b = blockIdx.x, j = threadIdx.x;
     if (b >= B) return;
@@ -221,7 +223,7 @@ extern "C" int ga_smpl_forward(int32_t B, const float *pose, const float *transl
     GA_REQUIRE(B >= 0, "bad batch %d", B);
     if (B == 0) return GA_OK;
     GA_REQUIRE(pose && transl && rest_joints && inv_cano && cano2live && saved_G, "NULL pointer argument");
-    { ProfScope _ps("smpl_fwd_kernel", static_cast<cudaStream_t>(stream_)); smpl_fwd_kernel<<<B, 32, 0, static_cast<cudaStream_t>(stream_)>>>(B, pose, transl, rest_joints, inv_cano, cano2live, saved_G); }
+    { ProfScope _ps("smpl_fwd_kernel", static_cast<cudaStream_t>(stream_)); launch_k(smpl_fwd_kernel, B, 32, 0, static_cast<cudaStream_t>(stream_), B, pose, transl, rest_joints, inv_cano, cano2live, saved_G); }
     GA_CHECK_LAUNCH("smpl_fwd_kernel");
     return GA_OK;
 }
@@ -232,7 +234,7 @@ extern "C" int ga_smpl_backward(int32_t B, const float *pose, const float *rest_
     GA_REQUIRE(B >= 0, "bad batch %d", B);
     if (B == 0) return GA_OK;
     GA_REQUIRE(pose && rest_joints && inv_cano && saved_G && d_cano2live && d_pose && d_transl, "NULL pointer argument");
-    { ProfScope _ps("smpl_bwd_kernel", static_cast<cudaStream_t>(stream_)); smpl_bwd_kernel<<<B, 32, 0, static_cast<cudaStream_t>(stream_)>>>(B, pose, rest_joints, inv_cano, saved_G, d_cano2live, d_pose, d_transl); }
+    { ProfScope _ps("smpl_bwd_kernel", static_cast<cudaStream_t>(stream_)); launch_k(smpl_bwd_kernel, B, 32, 0, static_cast<cudaStream_t>(stream_), B, pose, rest_joints, inv_cano, saved_G, d_cano2live, d_pose, d_transl); }
     GA_CHECK_LAUNCH("smpl_bwd_kernel");
     return GA_OK;
 }

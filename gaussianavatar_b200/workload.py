@@ -96,7 +96,9 @@ class Stage1Workload:
         if key not in cache:
             cache[key] = torch.tensor(ids, device=self.device)
         idx = cache[key]
-        return dict(pose_idx=idx, original_image=self.gt_dev[idx], **self.camera_fields(len(ids)))
+        B = len(ids)
+        img = self.gt_dev[ids[0]:ids[0] + B] if all(ids[j] == ids[0] + j for j in range(B)) else self.gt_dev[idx]     # a view when contiguous
+        return dict(pose_idx=idx, original_image=img, **self.camera_fields(B))
 
     def host_batch(self, ids):
         """The same batch as HOST tensors (pinned), as a DataLoader would hand it over (train.py:63-66)."""
