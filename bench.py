@@ -32,41 +32,74 @@ UNIT = "frames/s"
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line), in-process through NVML
+    (`pynvml`, three cheap queries every 50 ms from a daemon thread).  An external `nvidia-smi -lms 100` loop was measured to
+    stall kernel launches on some boxes of this pool (the same graph-replayed step took 5.2 .. 15 ms while it ran); it is only the
+    fallback when pynvml is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index: int):
-        self.gpu, self.rows, self._p = gpu_index, [], None
+        self.gpu, self.rows, self._p, self._stop, self._thr, self._h = gpu_index, [], None, False, None, None
 
     def start(self):
         try:
-            self._p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                        "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.gpu
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+            self._max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)      # static, and slow to query (4 ms avg, 25 ms max under load)
+
+            def loop():
+                nv, h = self._nv, self._h
+                while not self._stop:
+                    try:
+                        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                        mx = self._max_sm
+                        rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.rows.append((float(sm), float(mx), int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(0.05)
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
+            return
+        except Exception:
+            self._h = None
+        try:
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self._p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "250"],
+                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self._p = None
 
     def _read(self):
         for line in self._p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self) -> dict:
-        if self._p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self._p.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            c = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                bits = sum(bit for (name, bit), v in zip(self.REASONS, c[2:6]) if v.lower().startswith("active"))
+                self.rows.append((float(c[0]), float(c[1]), bits))
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+    def stop(self) -> dict:
+        self._stop = True
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        if self._p is not None:
+            time.sleep(0.3)
+            self._p.terminate()
+        if self._thr is None and self._p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = sorted({name for r in self.rows for name, bit in self.REASONS if r[2] & bit})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "how": "pynvml thread, 50 ms" if self._thr is not None else "nvidia-smi -lms 250"}
 
 
 def measured_peaks() -> dict:
@@ -217,6 +250,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.frames_per_gpu
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))      # everything below runs on one non-default stream (graph capture needs that)
 
     wl = Stage1Workload(args.config, B, device=dev)
     wl.make_ground_truth()
@@ -228,11 +262,36 @@ def main():
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    # every distinct batch of the frame pool is built on the device once, before anything is timed: "inputs already resident in HBM"
+    dev_batches = {}
+    for i in range(wl.num_frames):
+        ids = tuple(wl.frame_ids(i, rank, world))
+        if ids not in dev_batches:
+            dev_batches[ids] = wl.device_batch(list(ids))
+    torch.cuda.synchronize()
+
+    _sleep_ms = float(os.environ.get("GA_VALUE_SLEEP_MS", "0"))       # experiment hook (never set by the driver)
+    if os.environ.get("GA_VALUE_CLONE") == "1":
+        for b in dev_batches.values():
+            b["original_image"] = b["original_image"].clone()
+
     def run_value(n, start):
         t0 = time.perf_counter()
+        trainer.host_wait_s = trainer.host_enqueue_s = 0.0
+        diag_ev = [] if (os.environ.get("GA_BENCH_DIAG") == "1" and rank == 0 and n > 2) else None
         for i in range(n):
-            batch = wl.device_batch(wl.frame_ids(start + i, rank, world))
+            batch = dev_batches[tuple(wl.frame_ids(start + i, rank, world))]
+            if _sleep_ms:
+                time.sleep(_sleep_ms * 1e-3)
             trainer.step(batch, iteration0 + start + i, epoch=1)
+            if diag_ev is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); diag_ev.append(e)
+        if os.environ.get("GA_BENCH_DIAG") == "1" and rank == 0 and n > 2:
+            print(f"value diag: host wait-for-status {1e3 * trainer.host_wait_s / n:.2f} ms/step, enqueue {1e3 * trainer.host_enqueue_s / n:.2f} ms/step", file=sys.stderr, flush=True)
+        trainer.host_wait_s = trainer.host_enqueue_s = 0.0
+        if diag_ev:
+            torch.cuda.synchronize()
+            print("value diag per-step ms:", " ".join(f"{a.elapsed_time(b):.2f}" for a, b in zip(diag_ev[:-1], diag_ev[1:])), file=sys.stderr, flush=True)
         if os.environ.get("GA_BENCH_DIAG") == "1" and rank == 0 and n > 2:
             print(f"value diag (rank 0): host enqueue loop {1e3 * (time.perf_counter() - t0) / n:.2f} ms per step", file=sys.stderr, flush=True)
 
@@ -299,6 +358,27 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
+
+    # ---- launch-mode calibration (untimed, part of the warm-up) ----------------------------------------------------------
+    # The step runs either as ~120 eager launches or as ONE replayed CUDA graph (+ the optimizer launches).  Which is faster depends
+    # on the box: the replayed graph costs the device ~0.4 ms more per step than back-to-back stream launches (measured: 5.2-5.5 vs
+    # 4.7-4.9 ms), but a slow host cannot keep 120 launches per step ahead of the GPU (6.9 ms of enqueueing per step on one box of
+    # this pool).  Both compute the same thing (tests/test_train_gpu.py::test_graphed_step_matches_eager_step), so measure and pick.
+    calib = None
+    if os.environ.get("GA_STEP_GRAPH") is None and world == 1:
+        def ms_per_step(n, start):
+            torch.cuda.synchronize(); t = time.perf_counter()
+            run_value(n, start)
+            trainer.finish(); torch.cuda.synchronize()
+            return 1e3 * (time.perf_counter() - t) / n
+        trainer.use_graph = False
+        run_value(3, 0)
+        eager_ms = ms_per_step(10, 3)
+        trainer.use_graph = True
+        run_value(3, 13)                      # captures the graph
+        graph_ms = ms_per_step(10, 16)
+        trainer.use_graph = graph_ms < eager_ms
+        calib = {"eager_ms_per_step": round(eager_ms, 3), "graph_ms_per_step": round(graph_ms, 3), "chosen": "graph" if trainer.use_graph else "eager"}
 
     # ---- warm-up, then the timed region (inputs resident in HBM) -------------------------------------------------------
     clocks = ClockSampler(local)
@@ -400,10 +480,31 @@ def main():
     raster_fwd_ms = kms(*raster_fwd_names) / B          # per frame
     raster_bwd_ms = kms("render_bwd_kernel", "preprocess_bwd_kernel") / B
     raster_gbs = cost["raster_fwd_bytes"] / (raster_fwd_ms * 1e-3) / 1e9 if raster_fwd_ms > 0 else None
-    raster_roofline = {"kernel": "rasterizer forward K1-K6, per frame", "bound": "hbm", "achieved": raster_gbs, "peak": peaks["hbm_gbs"],
-                       "unit": "GB/s", "frac": raster_gbs / peaks["hbm_gbs"] if raster_gbs else None, "traffic": None,
+    raster_roofline = {"kernel": "rasterizer forward K1-K6, per frame (bytes: SURVEY.md §8d model of upstream's pipeline)", "bound": "hbm", "achieved": raster_gbs,
+                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": raster_gbs / peaks["hbm_gbs"] if raster_gbs else None, "traffic": None,
                        "algorithmic_bytes": cost["raster_fwd_bytes"], "ms_per_frame": raster_fwd_ms, "num_rendered": R,
                        "bwd_ms_per_frame": raster_bwd_ms, "peak_source": peaks["_source"]}
+    # per stage: the streaming stages against HBM with THIS pipeline's algorithmic bytes per frame,
+    # the compositing kernels as (pixel x list-entry) interactions per second — they are instruction / latency bound, not HBM bound
+    T_tiles = ((wl.side + 15) // 16) ** 2
+    stage_bytes = {"preprocess_fwd_kernel": wl.N * 100 + R * 4, "tile_scan_kernel": T_tiles * 28, "bucket_scatter_kernel": wl.N * 12 + R * 8,
+                   "tile_sort_kernel": R * 100, "preprocess_bwd_kernel": wl.N * 150}
+    raster_stages = {}
+    for k, nbytes in stage_bytes.items():
+        ms = kms(k) / B
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
+        raster_stages[k] = {"bound": "hbm", "ms_per_frame": ms, "algorithmic_bytes": nbytes, "achieved_gbs": gbs,
+                            "frac": gbs / peaks["hbm_gbs"] if gbs else None}
+    try:
+        pv = plan_views = wl.model._last_plan.views() if getattr(wl.model, "_last_plan", None) is not None else None
+        inter = float(sum(int(v["n_contrib"].to(torch.int64).sum()) for v in pv)) / max(1, len(pv)) if pv else None
+    except Exception:
+        inter = None
+    for k in ("render_fwd_kernel", "render_bwd_kernel"):
+        ms = kms(k) / B
+        raster_stages[k] = {"bound": "instruction issue / latency", "ms_per_frame": ms, "pixel_entry_interactions": inter,
+                            "ginteractions_per_s": inter / (ms * 1e-3) / 1e9 if (inter and ms > 0) else None}
+    raster_roofline["stages"] = raster_stages
 
     # ---- BASELINE configs 4 and 5 next to the headline ---------------------------------------------------
     extra = {}
@@ -431,9 +532,16 @@ def main():
         wl4.make_ground_truth()
         tr4 = Stage1Trainer(wl4.model, fused_adam=True)
 
+        batches4 = {}
+        for i in range(wl4.num_frames):
+            ids = tuple(wl4.frame_ids(i, rank, world))
+            if ids not in batches4:
+                batches4[ids] = wl4.device_batch(list(ids))
+        torch.cuda.synchronize()
+
         def run4(n, start=[0]):
             for i in range(n):
-                tr4.step(wl4.device_batch(wl4.frame_ids(start[0] + i, rank, world)), iteration0 + start[0] + i, epoch=1)
+                tr4.step(batches4[tuple(wl4.frame_ids(start[0] + i, rank, world))], iteration0 + start[0] + i, epoch=1)
             start[0] += n
         run4(max(3, args.warmup))
         ms4 = timed_loop(run4, args.steps)
@@ -525,7 +633,7 @@ def main():
                                        f"L1/SSIM), {B} frames/GPU/step, global batch {B * world}", "poses": wl.pose_source,
                            "l2_policy": "inputs and activations (>1.5 GB/step) exceed the 126 MB L2; no explicit flush",
                            "parallelism": f"dp{world} (frames sharded, 1 all-reduce of 1.56M fp32 grads)",
-                           "step_graph": step_graph_used},
+                           "step_graph": step_graph_used, "step_mode_calibration": calib},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "mlp_fwd_roofline": fwd_roofline, "raster_roofline": raster_roofline,
                 "cpu_baseline": cpu_baseline, **extra,
                 "kernel_ms_per_step": {k: round(v[1], 4) for k, v in sorted(per_step.items(), key=lambda kv: -kv[1][1])},

@@ -35,8 +35,12 @@ constexpr int kTile = 16;
 constexpr int kBlock = kTile * kTile;
 constexpr int kSeg = 256;            // list positions per checkpoint interval = per backward work item
 constexpr int kSortThreads = 512;
-constexpr int kSortMax = 8192;       // keys one CTA sorts in shared memory at a time (64 KB)
-constexpr int kStatusInts = 16;      // status[0] instances, [1] overflow flag, [2] segments, [4+b] first instance of frame b
+constexpr int kSortMax = 8192;       // keys one CTA sorts in shared memory at a time (64 KB): long tile lists (>= kSortSmallMax keys)
+constexpr int kSortSmallThreads = 128;
+constexpr int kSortSmallMax = 2048;  // short tile lists go to 128-thread CTAs (16 KB of keys, a dozen CTAs per SM): with 512 threads a
+                                     // 500-entry bucket is mostly barrier waits (barrier stall 25 per issue in ncu, 19 % issue-active)
+constexpr int kStatusInts = 16;      // status[0] instances, [1] overflow flag, [2] segments, [3] non-empty tiles, [4+b] first instance of
+                                     // frame b (b <= 8), [13] tiles with >= kSortSmallMax entries, [15] the caller's serial number
 
 struct Dims {
     int B, P, H, W, gx, gy, T;
@@ -427,6 +431,8 @@ tile_scan_kernel(int n, int T, long long capacity, const uint32_t *__restrict__ 
         uint32_t run = 0;
         for (int k = 32; k >= 0; --k) { cls_base[k] = run; run += cls_count[k]; }    // longest class first, empties last
         status[3] = (int32_t)cls_base[0];
+        static_assert(kSortSmallMax == 2048, "class boundary below assumes 2^11");
+        status[13] = (int32_t)cls_base[11];           // tiles of class >= 12 (count >= 2048) come first in `order`
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += 1024) {
@@ -529,7 +535,8 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t *keys, int n2)
 // order, the Gaussian index and the packed record the compositing kernels stream.  Buckets longer than kSortMax are sorted
 // kSortMax keys at a time (written back in place) and merged by rank: keys are unique, so an element's final position is
 // the number of smaller keys, i.e. the sum of its lower bounds in the sorted runs.
-__global__ void __launch_bounds__(kSortThreads)
+template <int kThreads, int kMax, bool kLong>
+__global__ void __launch_bounds__(kThreads)
 tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const uint32_t *__restrict__ order,
                  const uint2 *__restrict__ ranges, const uint32_t *__restrict__ seg_start,
                  uint64_t *__restrict__ bucket, const float2 *__restrict__ xy, const float4 *__restrict__ conic_o,
@@ -539,12 +546,16 @@ tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const
 {
     pdl_wait();
     extern __shared__ uint64_t s_keys[];
-    using BinScan = cub::BlockScan<uint32_t, kSortThreads>;
+    using BinScan = cub::BlockScan<uint32_t, kThreads>;
+    constexpr int kBins = 2 * kThreads;              // at most two depth bins per thread
     __shared__ typename BinScan::TempStorage s_scan;
-    __shared__ uint32_t s_hist[1025], s_off[1025], s_red[3];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BT; i += gridDim.x * blockDim.x) tile_maxc[i] = 0u;
-    const int nactive = status[3];
-    for (int it = blockIdx.x; it < nactive; it += gridDim.x) {
+    __shared__ uint32_t s_hist[kBins + 1], s_off[kBins + 1], s_red[3];
+    if (kLong)
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < BT; i += gridDim.x * blockDim.x) tile_maxc[i] = 0u;
+    // `order` lists the tiles by decreasing length class: the first status[13] have >= kSortSmallMax entries (this kernel's kLong
+    // instance), the rest up to status[3] are shorter (the 128-thread instance)
+    const int first = kLong ? 0 : status[13], last = kLong ? status[13] : status[3];
+    for (int it = first + blockIdx.x; it < last; it += gridDim.x) {
         const int blk = (int)order[it];
         const uint2 r = ranges[blk];
         const int n = (int)(r.y - r.x);
@@ -563,19 +574,28 @@ tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const
             recC[o] = make_float4(colors[3 * g], colors[3 * g + 1], colors[3 * g + 2], 0.f);
         };
 
-        if (n <= kSortMax) {
+        if (n <= kMax) {
             // Bucket-then-insertion: one counting pass over linear depth bins (about 8 entries each) puts every key within a few
             // places of its final position, one thread per bin finishes it by insertion — a fraction of the shared-memory traffic of
             // a full bitonic network.  Bins are monotone in depth, ties inside a bin are ordered by the full (depth bits, index) key,
             // so the result is the same total order.  Degenerate depth distributions (a bin above kMaxBin entries, e.g. many
             // equal depths) fall back to the bitonic network on the same buffer.
+            // The thread's keys (at most kPer = kMax / kThreads) are read from global memory ONCE, all loads in flight together, and
+            // stay in registers through the min/max, histogram and scatter passes: the kernel is bound by memory latency, not
+            // bandwidth (ncu: long_scoreboard on top, 12-14 % issue-active), so what counts is the number of dependent round trips.
             constexpr int kMaxBin = 48;
-            const int nb = n >= 64 ? min(1024, max(32, n >> 3)) : 0;
-            bool binned = false;
+            constexpr int kPer = kMax / kThreads;
+            uint64_t key[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) { const int i = threadIdx.x + k * kThreads; key[k] = i < n ? bucket[r.x + i] : ~0ull; }
+            const int nb = n >= 64 ? min(kBins, max(32, n >> 3)) : 0;
+            bool binned = false, filled = false;
             if (nb) {
                 uint32_t lo = 0xffffffffu, hi = 0u;
-                for (int i = threadIdx.x; i < n; i += blockDim.x) { const uint32_t d = (uint32_t)(bucket[r.x + i] >> 32); lo = min(lo, d); hi = max(hi, d); }
-                for (int i = threadIdx.x; i < 1025; i += blockDim.x) s_hist[i] = 0;
+#pragma unroll
+                for (int k = 0; k < kPer; ++k)
+                    if (threadIdx.x + k * kThreads < n) { const uint32_t d = (uint32_t)(key[k] >> 32); lo = min(lo, d); hi = max(hi, d); }
+                for (int i = threadIdx.x; i < kBins + 1; i += blockDim.x) s_hist[i] = 0;
                 if (threadIdx.x == 0) { s_red[0] = 0xffffffffu; s_red[1] = 0u; s_red[2] = 0u; }
                 __syncthreads();
 #pragma unroll
@@ -585,10 +605,12 @@ tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const
                 const float dmin = __uint_as_float(s_red[0]), dmax = __uint_as_float(s_red[1]);      // depths are positive: bit order = value order
                 if (dmax > dmin) {
                     const float scale = (float)nb / (dmax - dmin);
-                    auto bin_of = [&](uint64_t key) { return min(nb - 1, (int)((__uint_as_float((uint32_t)(key >> 32)) - dmin) * scale)); };
-                    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&s_hist[bin_of(bucket[r.x + i])], 1u);
+                    auto bin_of = [&](uint64_t kk) { return min(nb - 1, (int)((__uint_as_float((uint32_t)(kk >> 32)) - dmin) * scale)); };
+#pragma unroll
+                    for (int k = 0; k < kPer; ++k)
+                        if (threadIdx.x + k * kThreads < n) atomicAdd(&s_hist[bin_of(key[k])], 1u);
                     __syncthreads();
-                    // exclusive scan of the bin counts (nb <= 1024 <= 2 per thread) and their maximum
+                    // exclusive scan of the bin counts (nb <= 2 per thread) and their maximum
                     uint32_t c0 = 2 * threadIdx.x < nb ? s_hist[2 * threadIdx.x] : 0u, c1 = 2 * threadIdx.x + 1 < nb ? s_hist[2 * threadIdx.x + 1] : 0u;
                     uint32_t ex;
                     BinScan(s_scan).ExclusiveSum(c0 + c1, ex);
@@ -598,19 +620,19 @@ tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const
                     if (2 * threadIdx.x + 1 < nb) { s_off[2 * threadIdx.x + 1] = ex + c0; s_hist[2 * threadIdx.x + 1] = ex + c0; }
                     if (threadIdx.x == 0) s_off[nb] = (uint32_t)n;
                     __syncthreads();
-                    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                        const uint64_t key = bucket[r.x + i];
-                        s_keys[atomicAdd(&s_hist[bin_of(key)], 1u)] = key;
-                    }
+#pragma unroll
+                    for (int k = 0; k < kPer; ++k)
+                        if (threadIdx.x + k * kThreads < n) s_keys[atomicAdd(&s_hist[bin_of(key[k])], 1u)] = key[k];
+                    filled = true;
                     __syncthreads();
                     if (s_red[2] == 0u) {
                         for (int bi = threadIdx.x; bi < nb; bi += blockDim.x) {
                             const int b0 = (int)s_off[bi], b1 = (int)s_off[bi + 1];
                             for (int i = b0 + 1; i < b1; ++i) {
-                                const uint64_t key = s_keys[i];
+                                const uint64_t kk = s_keys[i];
                                 int j = i - 1;
-                                while (j >= b0 && s_keys[j] > key) { s_keys[j + 1] = s_keys[j]; --j; }
-                                s_keys[j + 1] = key;
+                                while (j >= b0 && s_keys[j] > kk) { s_keys[j + 1] = s_keys[j]; --j; }
+                                s_keys[j + 1] = kk;
                             }
                         }
                         __syncthreads();
@@ -621,18 +643,45 @@ tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const
             if (!binned) {
                 int n2 = 32;
                 while (n2 < n) n2 <<= 1;
-                if (!nb || !(__uint_as_float(s_red[1]) > __uint_as_float(s_red[0])))          // s_keys not filled by the scatter pass
-                    for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = bucket[r.x + i];
+                if (!filled) {
+#pragma unroll
+                    for (int k = 0; k < kPer; ++k) { const int i = threadIdx.x + k * kThreads; if (i < n) s_keys[i] = key[k]; }
+                }
                 for (int i = n + threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = ~0ull;
                 __syncthreads();
                 bitonic_sort_smem(s_keys, n2);
             }
-            for (int i = threadIdx.x; i < n; i += blockDim.x) emit(i, s_keys[i]);
+            // emit four list entries per thread at a time: the 4 x 5 gathers they need are independent and in flight together
+            for (int i0 = 0; i0 < n; i0 += 4 * kThreads) {
+                uint64_t kk[4]; float2 c[4]; float4 co[4]; float col[4][3];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + threadIdx.x + u * kThreads;
+                    kk[u] = i < n ? s_keys[i] : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const size_t g = gbase + (uint32_t)kk[u];
+                    c[u] = xy[g]; co[u] = conic_o[g];
+                    col[u][0] = colors[3 * g]; col[u][1] = colors[3 * g + 1]; col[u][2] = colors[3 * g + 2];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + threadIdx.x + u * kThreads;
+                    if (i < n) {
+                        const size_t o = (size_t)r.x + i;
+                        point_list[o] = (uint32_t)kk[u];
+                        recA[o] = make_float4(c[u].x, c[u].y, cull_radius2(co[u]), __uint_as_float((uint32_t)kk[u]));
+                        recB[o] = co[u];
+                        recC[o] = make_float4(col[u][0], col[u][1], col[u][2], 0.f);
+                    }
+                }
+            }
             __syncthreads();                 // s_keys is reloaded by the next tile
             continue;
         }
-        for (int c0 = 0; c0 < n; c0 += kSortMax) {
-            const int m = min(kSortMax, n - c0);
+        for (int c0 = 0; c0 < n; c0 += kMax) {
+            const int m = min(kMax, n - c0);
             int n2 = 32;
             while (n2 < m) n2 <<= 1;
             for (int i = threadIdx.x; i < n2; i += blockDim.x) s_keys[i] = i < m ? bucket[r.x + c0 + i] : ~0ull;
@@ -644,9 +693,9 @@ tile_sort_kernel(int P, int T, int BT, const int32_t *__restrict__ status, const
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const uint64_t key = bucket[r.x + i];
             int rank = 0;
-            for (int c0 = 0; c0 < n; c0 += kSortMax) {
+            for (int c0 = 0; c0 < n; c0 += kMax) {
                 const uint64_t *run = bucket + r.x + c0;
-                int lo = 0, hi = min(kSortMax, n - c0);
+                int lo = 0, hi = min(kMax, n - c0);
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
                     if (run[mid] < key) lo = mid + 1; else hi = mid;
@@ -841,7 +890,7 @@ render_bwd_kernel(int H, int W, int gx, int T_tiles, int P, const int32_t *__res
 {
     pdl_wait();
     __shared__ float4 s_a[kSeg], s_b[kSeg], s_c[kSeg];
-    __shared__ float s_acc[9][kSeg];
+    __shared__ float s_acc[9][kSeg + 1];      // + 1: the 8 lanes that own a Gaussian's 8 sums hit 8 different banks
 
     const int g = blockIdx.x;
     if (g >= status[2]) return;
@@ -1148,7 +1197,8 @@ int launch_binning_and_render(const Dims &d, const FwdArgs &a, long long capacit
 {
     static bool attr_set = false;
     if (!attr_set) {
-        GA_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortMax * (int)sizeof(uint64_t)));
+        GA_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_kernel<kSortThreads, kSortMax, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSortMax * (int)sizeof(uint64_t)));
         attr_set = true;
     }
     const int BT = d.B * d.T;
@@ -1162,9 +1212,13 @@ int launch_binning_and_render(const Dims &d, const FwdArgs &a, long long capacit
     }
     {
         ProfScope _ps("tile_sort_kernel", stream);
-        launch_k(tile_sort_kernel, min(BT, 3 * num_sms()), kSortThreads, kSortMax * sizeof(uint64_t), stream, 
-            d.P, d.T, BT, iv.status, iv.order, iv.ranges, iv.seg_start, bv.bucket, g.xy, g.conic_o, a.colors, bv.point_list, bv.recA, bv.recB,
-            bv.recC, bv.seg_tile, iv.tile_maxc);
+        launch_k(tile_sort_kernel<kSortThreads, kSortMax, true>, min(BT, 3 * num_sms()), kSortThreads, kSortMax * sizeof(uint64_t), stream,
+                 d.P, d.T, BT, iv.status, iv.order, iv.ranges, iv.seg_start, bv.bucket, g.xy, g.conic_o, a.colors, bv.point_list, bv.recA, bv.recB,
+                 bv.recC, bv.seg_tile, iv.tile_maxc);
+        count_launch();
+        launch_k(tile_sort_kernel<kSortSmallThreads, kSortSmallMax, false>, min(BT, 12 * num_sms()), kSortSmallThreads,
+                 kSortSmallMax * sizeof(uint64_t), stream, d.P, d.T, BT, iv.status, iv.order, iv.ranges, iv.seg_start, bv.bucket, g.xy, g.conic_o,
+                 a.colors, bv.point_list, bv.recA, bv.recB, bv.recC, bv.seg_tile, iv.tile_maxc);
     }
     GA_CHECK_LAUNCH("tile_sort_kernel");
     {

@@ -237,9 +237,11 @@ class RasterBatchPlan:
         count) and False is returned: the caller must run the step again."""
         if not self.pending:
             return True
+        import time
         while int(self.status_host[15]) != self.serial:      # the copy behind the latest forward has not landed yet
             if not wait:
                 return True          # not known yet; ask again later
+            time.sleep(5e-5)         # yield the core: a hot spin starves the driver's own threads on boxes with few CPUs
         self.pending = False
         if int(self.status_host[1]) == 0:
             return True

@@ -52,6 +52,7 @@ class Stage1Trainer:
         # whole-step CUDA graph (forward + loss + backward in ONE launch; all-reduce and Adam follow eagerly): on unless GA_STEP_GRAPH=0
         self.use_graph = (os.environ.get("GA_STEP_GRAPH", "1") != "0") if use_graph is None else bool(use_graph)
         self._graphs = {}
+        self.host_wait_s = self.host_enqueue_s = 0.0
         self.replayed_launches = 0      # kernels of this library launched through graph replays (ga_launch_count sees only eager launches)
         self.opt = model.opt_parms
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -152,14 +153,20 @@ class Stage1Trainer:
         """One optimisation step.  The batched rasterizer never makes the host wait for the device: whether the step's binning
         buffer was large enough is known one step later (the device flag also turns that step's Adam launches into no-ops), so
         an overflowed step is detected here, before the next one, and simply run again with the grown buffer."""
+        import time as _time
+        t0 = _time.perf_counter()
         prev = getattr(self, "_prev", None)
         if prev is not None and not self._step_fitted():
             self._undo_host_step(prev[2])
             self._step_once(*prev)
             if not self._step_fitted():
                 raise RuntimeError("batched rasterizer: binning buffer overflowed twice in a row")
+        t1 = _time.perf_counter()
         self._prev = (batch, iteration, epoch)
-        return self._step_once(batch, iteration, epoch)
+        out = self._step_once(batch, iteration, epoch)
+        self.host_wait_s += t1 - t0                      # waiting for the previous step's rasterizer status (the GPU is busy meanwhile)
+        self.host_enqueue_s += _time.perf_counter() - t1  # enqueueing this step
+        return out
 
     def finish(self):
         """Settle the last step (re-run it if its binning buffer overflowed)."""
@@ -292,6 +299,23 @@ class Stage1Trainer:
         return G.loss
 
     def _step_once(self, batch, iteration: int, epoch: int = 0):
+        """Runs the step on a dedicated non-default stream when the caller sits on the default one: autograd ties each parameter's
+        AccumulateGrad node to the stream of its first backward, and a node tied to the legacy default stream makes every later graph
+        capture illegal (the engine would have to synchronise with stream 0 inside the capture)."""
+        m = self.model
+        if self.use_graph and m.device.type == "cuda":
+            cur = torch.cuda.current_stream(m.device)
+            if cur == torch.cuda.default_stream(m.device):
+                if getattr(self, "_stream", None) is None:
+                    self._stream = torch.cuda.Stream(device=m.device)
+                self._stream.wait_stream(cur)
+                with torch.cuda.stream(self._stream):
+                    out = self._step_impl(batch, iteration, epoch)
+                cur.wait_stream(self._stream)
+                return out
+        return self._step_impl(batch, iteration, epoch)
+
+    def _step_impl(self, batch, iteration: int, epoch: int = 0):
         m = self.model
         if self._graph_applicable(batch, iteration, epoch):
             loss = self._step_graphed(batch, iteration, epoch)
