@@ -303,31 +303,39 @@ __device__ __forceinline__ void for_each_tile_balanced(const ushort4 rc, int gx,
     }
 }
 
-// The tile bounding box of a CTA's rects (x0, y0, width, height in tiles; width = 0 if every rect is empty), through shared memory.
-constexpr int kHistTiles = 10240;    // tiles a CTA-local histogram covers (40 KB): a CTA's 256 Gaussians are neighbours on screen
-__device__ __forceinline__ int4 cta_tile_bbox(const ushort4 rc, uint32_t *s_box /*[4]*/)
+// CTA-local tile table of K1 / K3: an open-addressing hash (tile id -> count / cursor) in shared memory.  A CTA's 256 Gaussians touch
+// at most a few thousand distinct tiles wherever they lie on screen, so the table is small (kTileSlots), independent of the image
+// size and of how the Gaussians are ordered; an instance whose probe sequence is full (huge Gaussians) falls back to the global
+// atomic, consistently in every pass (slots are never freed, so the same probes fail again).
+constexpr int kTileSlots = 4096;
+constexpr uint32_t kEmptySlot = 0xffffffffu;
+__device__ __forceinline__ int tile_slot_insert(uint32_t *s_key, uint32_t tile)
 {
-    if (threadIdx.x == 0) { s_box[0] = 0xffffu; s_box[1] = 0xffffu; s_box[2] = 0u; s_box[3] = 0u; }
-    __syncthreads();
-    uint32_t x0 = 0xffffu, y0 = 0xffffu, x1 = 0u, y1 = 0u;
-    if (rc.z > rc.x && rc.w > rc.y) { x0 = rc.x; y0 = rc.y; x1 = rc.z; y1 = rc.w; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o)); y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
-        x1 = max(x1, __shfl_xor_sync(0xffffffffu, x1, o)); y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    uint32_t slot = (tile * 2654435761u) >> 20;                 // 12 bits
+    for (int tries = 0; tries < 48; ++tries) {
+        const uint32_t prev = atomicCAS(&s_key[slot], kEmptySlot, tile);
+        if (prev == kEmptySlot || prev == tile) return (int)slot;
+        slot = (slot + 1) & (kTileSlots - 1);
     }
-    if ((threadIdx.x & 31) == 0 && x1 > x0) { atomicMin(&s_box[0], x0); atomicMin(&s_box[1], y0); atomicMax(&s_box[2], x1); atomicMax(&s_box[3], y1); }
-    __syncthreads();
-    const int bx0 = (int)s_box[0], by0 = (int)s_box[1], bx1 = (int)s_box[2], by1 = (int)s_box[3];
-    return bx1 > bx0 ? make_int4(bx0, by0, bx1 - bx0, by1 - by0) : make_int4(0, 0, 0, 0);
+    return -1;
+}
+__device__ __forceinline__ int tile_slot_find(const uint32_t *s_key, uint32_t tile)
+{
+    uint32_t slot = (tile * 2654435761u) >> 20;
+    for (int tries = 0; tries < 48; ++tries) {
+        const uint32_t k = s_key[slot];
+        if (k == tile) return (int)slot;
+        if (k == kEmptySlot) return -1;
+        slot = (slot + 1) & (kTileSlots - 1);
+    }
+    return -1;
 }
 
 // K1: one thread per Gaussian (blockIdx.y = frame).  Besides the per-Gaussian state it counts, per tile, the instances the
 // tile will receive (tile_count[frame][tile]): the binning that follows is a bucket sort by tile, not a global sort.
-// The CTA's 256 Gaussians (neighbours in UV space, so neighbours on screen) first count into a shared-memory histogram over their
-// common tile bounding box and then add only its non-zero bins to the global counters — a few hundred thousand atomics on a few
-// hundred hot addresses (which serialise in L2 and used to set this kernel's duration) become a few tens per CTA.  A CTA whose
-// bounding box exceeds the histogram (huge Gaussians) counts straight into global memory.
+// The CTA's 256 Gaussians first count into a shared-memory tile table and then add only its occupied slots to the global counters — a
+// few hundred thousand atomics on a few hundred hot addresses (which serialise in L2 and used to set this kernel's duration)
+// become one per (CTA, touched tile).
 template <bool kSmemHist>
 __global__ void __launch_bounds__(256)
 preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, CamSrc cam, float mod, const float *__restrict__ means3D,
@@ -352,19 +360,19 @@ preprocess_fwd_kernel(int P, int H, int W, int gx, int gy, CamSrc cam, float mod
                             rots + (size_t)b * rot_stride + 4 * (size_t)il, opac[(size_t)b * opac_stride + il], depth, xy, conic_o, cov3d,
                             tiles, rect, radii);
     uint32_t *tc = tile_count + (size_t)b * gx * gy;
-    __shared__ uint32_t s_hist[kHistTiles], s_box[4];
-    const int4 box = cta_tile_bbox(rc, s_box);
-    const int area = box.z * box.w;
-    if (kSmemHist && area > 0 && area <= kHistTiles) {
-        for (int t = threadIdx.x; t < area; t += blockDim.x) s_hist[t] = 0u;
+    if (kSmemHist) {
+        __shared__ uint32_t s_key[kTileSlots], s_cnt[kTileSlots];
+        for (int t = threadIdx.x; t < kTileSlots; t += blockDim.x) { s_key[t] = kEmptySlot; s_cnt[t] = 0u; }
         __syncthreads();
         for_each_tile_balanced(rc, gx, 0ull, [&](uint32_t tile, uint64_t) {
-            atomicAdd(&s_hist[((int)tile / gx - box.y) * box.z + (int)tile % gx - box.x], 1u);
+            const int slot = tile_slot_insert(s_key, tile);
+            if (slot >= 0) atomicAdd(&s_cnt[slot], 1u);
+            else atomicAdd(&tc[tile], 1u);
         });
         __syncthreads();
-        for (int t = threadIdx.x; t < area; t += blockDim.x) {
-            const uint32_t c = s_hist[t];
-            if (c) atomicAdd(&tc[(box.y + t / box.z) * gx + box.x + t % box.z], c);
+        for (int t = threadIdx.x; t < kTileSlots; t += blockDim.x) {
+            const uint32_t c = s_cnt[t];
+            if (c) atomicAdd(&tc[s_key[t]], c);
         }
     } else {
         for_each_tile_balanced(rc, gx, 0ull, [&](uint32_t tile, uint64_t) { atomicAdd(&tc[tile], 1u); });
@@ -464,22 +472,23 @@ bucket_scatter_kernel(int P, int gx, int T, long long capacity, const float *__r
         }
     }
     uint32_t *cur = cursor + (size_t)b * T;
-    __shared__ uint32_t s_hist[kHistTiles], s_box[4];          // counts, then the next place inside the CTA's run of each tile
-    const int4 box = cta_tile_bbox(rc, s_box);
-    const int area = box.z * box.w;
-    if (kSmemHist && area > 0 && area <= kHistTiles) {
-        auto local = [&](uint32_t tile) { return ((int)tile / gx - box.y) * box.z + (int)tile % gx - box.x; };
-        for (int t = threadIdx.x; t < area; t += blockDim.x) s_hist[t] = 0u;
+    if (kSmemHist) {
+        __shared__ uint32_t s_key[kTileSlots], s_cnt[kTileSlots];   // counts, then the next place inside the CTA's run of each tile
+        for (int t = threadIdx.x; t < kTileSlots; t += blockDim.x) { s_key[t] = kEmptySlot; s_cnt[t] = 0u; }
         __syncthreads();
-        for_each_tile_balanced(rc, gx, 0ull, [&](uint32_t tile, uint64_t) { atomicAdd(&s_hist[local(tile)], 1u); });
+        for_each_tile_balanced(rc, gx, 0ull, [&](uint32_t tile, uint64_t) {
+            const int slot = tile_slot_insert(s_key, tile);
+            if (slot >= 0) atomicAdd(&s_cnt[slot], 1u);
+        });
         __syncthreads();
-        for (int t = threadIdx.x; t < area; t += blockDim.x) {
-            const uint32_t c = s_hist[t];
-            if (c) s_hist[t] = atomicAdd(&cur[(box.y + t / box.z) * gx + box.x + t % box.z], c);
+        for (int t = threadIdx.x; t < kTileSlots; t += blockDim.x) {
+            const uint32_t c = s_cnt[t];
+            if (c) s_cnt[t] = atomicAdd(&cur[s_key[t]], c);
         }
         __syncthreads();
         for_each_tile_balanced(rc, gx, key, [&](uint32_t tile, uint64_t k) {
-            const uint32_t pos = atomicAdd(&s_hist[local(tile)], 1u);
+            const int slot = tile_slot_find(s_key, tile);
+            const uint32_t pos = slot >= 0 ? atomicAdd(&s_cnt[slot], 1u) : atomicAdd(&cur[tile], 1u);
             if ((long long)pos < capacity) bucket[pos] = k;
         });
     } else {
