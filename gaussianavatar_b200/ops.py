@@ -121,6 +121,11 @@ class DecoderNet(torch.autograd.Function):
                                         _stream()), "ga_decoder_forward")
         if state.track_running:
             state.num_batches_tracked += 1
+        # the activations live in ONE workspace per decoder state, not per autograd graph: stamp the forward so that a backward that
+        # arrives after a later forward on the same state (a second loss(), a logging render, retain_graph reuse) fails loudly
+        # instead of differentiating through the wrong activations
+        state.generation = getattr(state, "generation", 0) + 1
+        ctx.generation = state.generation
         ctx.state = state
         ctx.geo_shape = geo_feature.shape
         ctx.pose_shape = None if pose_feat is None else pose_feat.shape
@@ -131,6 +136,9 @@ class DecoderNet(torch.autograd.Function):
     def backward(ctx, d_dec):
         flat, dec = ctx.saved_tensors
         state = ctx.state
+        if ctx.generation != state.generation:
+            raise RuntimeError("DecoderNet.backward: the decoder ran forward again on the same (S, feat_res, batch) state since this graph was "
+                               "built; its activation workspace has been overwritten (run backward before the next forward)")
         d_dec = _f32c(d_dec)
         d_flat = torch.empty_like(flat)
         d_geo = torch.empty(ctx.geo_shape, device=flat.device, dtype=torch.float32)

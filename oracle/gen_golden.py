@@ -186,6 +186,29 @@ def gen_unet():
                         bn2_running_mean=net.conv2.bn.running_mean.numpy())
 
 
+def gen_unet_full_size():
+    """The reference's UnetNoCond5DS at the size GaussianAvatar instantiates it (input_nc=3, output_nc=64, nf=32, 128 x 128 position
+    maps, model/avatar_model.py:139-146): sub-sampled output / gradients keep the fixture small."""
+    from model.modules import UnetNoCond5DS                # reference
+    nf, cin, cout, side, B, seed = 32, 3, 64, 128, 2, 12
+    net = UnetNoCond5DS(input_nc=cin, output_nc=cout, nf=nf, up_mode="upconv", use_dropout=False)
+    missing, unexpected = net.load_state_dict(seeded_unet_params(seed, cin, cout, nf), strict=False)
+    assert not unexpected and all("running" in k or "num_batches" in k for k in missing), (missing, unexpected)
+    net.train()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, cin, side, side, generator=g).requires_grad_(True)
+    gout = torch.randn(B, cout, side, side, generator=g)
+    y = net(x)
+    (y * gout).sum().backward()
+    grads = dict(net.named_parameters())
+    np.savez_compressed(os.path.join(OUT, "unet5ds_nf32_s128.npz"), nf=nf, cin=cin, cout=cout, side=side, B=B, seed=seed,
+                        y_sub=y.detach().numpy()[:, :, ::8, ::8], y_norm=float(y.detach().norm()), dx_sub=x.grad.numpy()[:, :, ::4, ::4],
+                        dx_norm=float(x.grad.norm()), d_conv3_sub=grads["conv3.conv.weight"].grad.numpy()[:16, :16],
+                        d_upconv4_sub=grads["upconv4.up.weight"].grad.numpy()[:16, :16], d_bias=grads["upconv5.up.bias"].grad.numpy(),
+                        grad_norms=np.array([float(grads[k].grad.norm()) for k in sorted(grads)]), grad_names=np.array(sorted(grads)),
+                        bn2_running_mean=net.conv2.bn.running_mean.numpy())
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_test_pose_subset()
@@ -195,6 +218,7 @@ if __name__ == "__main__":
     gen_camera()
     gen_param_order()
     gen_unet()
+    gen_unet_full_size()
     gen_dataset_items()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

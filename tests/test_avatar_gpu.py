@@ -406,3 +406,16 @@ def test_train_stage2_end_to_end_vs_oracle_chain(tmp_path):
     with torch.no_grad():
         out = m.render_free_stage2(batch, 3000)
     assert out.shape == (B, 3, side, side) and torch.isfinite(out).all()
+
+
+def test_decoder_backward_after_a_newer_forward_fails_loudly():
+    """the decoder's activations live in one workspace per state; a stale backward must raise, not silently use them."""
+    from gaussianavatar_b200.network import POP_no_unet
+    net = POP_no_unet(c_geom=64, hsize=128).to(DEV)
+    geo = (torch.randn(1, 64, 16, 16) * 0.01).to(DEV).requires_grad_(True)
+    d1 = net.forward_packed(geo, 32, 1)
+    d2 = net.forward_packed(geo, 32, 1)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        d1.sum().backward()
+    d2.sum().backward()
+    assert torch.isfinite(net.flat.grad).all()

@@ -162,3 +162,35 @@ def test_product_pose_encoder_matches_reference_fixture():
         assert np.abs(grads[name].grad.numpy() - ref).max() < 2e-4 * max(1.0, np.abs(ref).max()), name
     assert np.abs(net.conv2.bn.running_mean.numpy() - d["bn2_running_mean"]).max() < 1e-6
     assert int(net.conv2.bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("which", ["oracle", "product"])
+def test_pose_encoder_at_the_reference_size_nf32_128(which):
+    """input_nc=3, output_nc=64, nf=32 on 128 x 128 position maps (what model/avatar_model.py:139-146 builds): the oracle restatement
+    and the product module against the reference module's (sub-sampled) outputs and gradients."""
+    d = np.load(os.path.join(GOLD, "unet5ds_nf32_s128.npz"))
+    nf, cin, cout, side, B, seed = (int(d[k]) for k in ("nf", "cin", "cout", "side", "B", "seed"))
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, cin, side, side, generator=g).requires_grad_(True)
+    gout = torch.randn(B, cout, side, side, generator=g)
+    params = ao.seeded_unet_params(seed, cin, cout, nf)
+    if which == "oracle":
+        p = {k: v.requires_grad_(True) for k, v in params.items()}
+        y = ao.unet5ds_forward(p, x)
+        grad_of = lambda name: p[name].grad
+    else:
+        from gaussianavatar_b200.pose_encoder import UnetNoCond5DS
+        net = UnetNoCond5DS(input_nc=cin, output_nc=cout, nf=nf, up_mode="upconv", use_dropout=False)
+        net.load_state_dict(params, strict=False)
+        y = net(x)
+        named = dict(net.named_parameters())
+        grad_of = lambda name: named[name].grad
+    (y * gout).sum().backward()
+    rel = lambda a, b: np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30)
+    assert rel(y.detach().numpy()[:, :, ::8, ::8], d["y_sub"]) < 1e-4 and abs(float(y.detach().norm()) - float(d["y_norm"])) < 1e-3 * float(d["y_norm"])
+    assert rel(x.grad.numpy()[:, :, ::4, ::4], d["dx_sub"]) < 2e-3
+    assert rel(grad_of("conv3.conv.weight").numpy()[:16, :16], d["d_conv3_sub"]) < 2e-3
+    assert rel(grad_of("upconv4.up.weight").numpy()[:16, :16], d["d_upconv4_sub"]) < 2e-3
+    assert rel(grad_of("upconv5.up.bias").numpy(), d["d_bias"]) < 2e-3
+    norms = np.array([float(grad_of(str(n)).norm()) for n in d["grad_names"]])
+    assert np.abs(norms - d["grad_norms"]).max() / d["grad_norms"].max() < 2e-3
