@@ -39,14 +39,37 @@ ssim_l1_fwd_kernel(int H, int W, const float *__restrict__ img, const float *__r
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTX + tx;
     const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
     const size_t plane = (size_t)blockIdx.z * H * W;
+    bool same = true;
     for (int i = tid; i < kSY * kSX; i += kTX * kTY) {
         const int ly = i / kSX, lx = i % kSX;
         const int y = y0 + ly - kHalo, x = x0 + lx - kHalo;
         float a = 0.f, b = 0.f;
         if (x >= 0 && x < W && y >= 0 && y < H) { a = img[plane + (size_t)y * W + x]; b = gt[plane + (size_t)y * W + x]; }
         sA[ly][lx] = a; sB[ly][lx] = b;
+        same = same && (a == b);
     }
-    __syncthreads();
+    // A tile whose whole window support shows image == target (the white background of GaussianAvatar's frames: most of the image)
+    // has SSIM == 1 and L1 == 0 at every pixel, and its three derivative maps are zero up to the round-off of terms that cancel
+    // (2 mu / C - 2 mu / C): write exact zeros and skip the 11x11 blurs.
+    if (__syncthreads_and(same)) {
+        const int x = x0 + tx, y = y0 + ty;
+        float one = 0.f;
+        if (x < W && y < H) {
+            const size_t p = plane + (size_t)y * W + x;
+            dm_dmu1[p] = 0.f; dm_ds1[p] = 0.f; dm_ds12[p] = 0.f;
+            one = 1.f;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) one += __shfl_xor_sync(0xffffffffu, one, o);
+        if ((tid & 31) == 0) sred[0][tid >> 5] = one;
+        __syncthreads();
+        if (tid == 0) {
+            float sum = 0.f;
+            for (int i = 0; i < kTX * kTY / 32; ++i) sum += sred[0][i];
+            atomicAdd(&acc[0], (double)sum);
+        }
+        return;
+    }
     // horizontal pass over all staged rows
     for (int i = tid; i < kSY * kTX; i += kTX * kTY) {
         const int ly = i / kTX, lx = i % kTX;
@@ -107,6 +130,7 @@ ssim_l1_bwd_kernel(int H, int W, const float *__restrict__ img, const float *__r
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * kTX + tx;
     const int x0 = blockIdx.x * kTX, y0 = blockIdx.y * kTY;
     const size_t plane = (size_t)blockIdx.z * H * W;
+    bool zero = true;
     for (int i = tid; i < kSY * kSX; i += kTX * kTY) {
         const int ly = i / kSX, lx = i % kSX;
         const int y = y0 + ly - kHalo, x = x0 + lx - kHalo;
@@ -116,8 +140,18 @@ ssim_l1_bwd_kernel(int H, int W, const float *__restrict__ img, const float *__r
             a = dm_dmu1[p]; b = dm_ds1[p]; c = dm_ds12[p];
         }
         sM[0][ly][lx] = a; sM[1][ly][lx] = b; sM[2][ly][lx] = c;
+        zero = zero && (a == 0.f) && (b == 0.f) && (c == 0.f);
     }
-    __syncthreads();
+    // all three derivative maps vanish over the window support (background tiles, see the forward): only the L1 term is left
+    if (__syncthreads_and(zero)) {
+        const int x = x0 + tx, y = y0 + ty;
+        if (x < W && y < H) {
+            const size_t p = plane + (size_t)y * W + x;
+            const float d = img[p] - gt[p];
+            d_img[p] = coef[0] * ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f));
+        }
+        return;
+    }
     for (int i = tid; i < kSY * kTX; i += kTX * kTY) {
         const int ly = i / kTX, lx = i % kTX;
         float a = 0.f, b = 0.f, c = 0.f;

@@ -46,6 +46,27 @@ def test_losses_vs_oracle_odd_sizes(shape):
     assert _rel(ad.grad.cpu().numpy() / 1.7, a64.grad.numpy()) < 2e-4
 
 
+def test_losses_with_uniform_background_tiles_vs_oracle():
+    """Frames whose background equals the target exactly (GaussianAvatar's white background): the kernels skip the blurs for tiles whose
+    whole window support is identical; loss and gradient still match the fp64 oracle."""
+    from gaussianavatar_b200.losses import image_loss
+    g = torch.Generator().manual_seed(5)
+    H, W = 160, 224
+    gt = torch.ones(2, 3, H, W)
+    gt[:, :, 40:120, 60:150] = torch.rand(2, 3, 80, 90, generator=g)
+    img = gt.clone()
+    img[:, :, 50:130, 70:170] = torch.rand(2, 3, 80, 100, generator=g)          # differs from gt inside and partly outside the figure
+    a64 = img.double().requires_grad_(True)
+    ref = 0.8 * ao.l1_loss_w(a64, gt.double()) + 0.2 * (1 - ao.ssim(a64, gt.double()))
+    ref.backward()
+    ad = img.to(DEV).requires_grad_(True)
+    loss = image_loss(ad, gt.to(DEV), 0.2)
+    loss.backward()
+    assert abs(loss.item() - ref.item()) < 2e-6
+    assert _rel(ad.grad.cpu().numpy(), a64.grad.numpy()) < 2e-4
+    assert (ad.grad[:, :, :20, :20] == 0).all()                                  # far background: exactly nothing
+
+
 def test_fused_adam_matches_torch_adam():
     from gaussianavatar_b200.optim import FusedAdam
     g = torch.Generator().manual_seed(0)
