@@ -42,13 +42,6 @@ struct alignas(1024) ConvSmem {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16u : 0u) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 __device__ __forceinline__ float round_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 
 // byte offset of 16-byte unit v (0..7) of row r inside a [rows][128 B] MN-major chunk (32-byte-base 128 B swizzle)

@@ -20,6 +20,7 @@
 // SURVEY.md §8 a-4); the strict-FP32 CUDA-core path (gemm.cuh) remains selectable and is the GPU-side reference.
 #include "gemm.cuh"
 #include "tc_common.cuh"
+#include <type_traits>
 
 // timing-ablation switches for tools/variants.py (never set in the product build): 1 no global loads in the producers, 2 no activation
 // math, 4 no MMA issue, 8 no epilogue math, 16 no epilogue global traffic
@@ -34,6 +35,13 @@
 #define TWAIT(slot, call) do { const long long t0_ = clock64(); call; tw_[slot] += clock64() - t0_; } while (0)
 #else
 #define TWAIT(slot, call) call
+#endif
+#if GA_TC_TIMING
+#define TMARK(var) const long long var = clock64()
+#define TADD(slot, var) tw_[slot] += clock64() - var
+#else
+#define TMARK(var)
+#define TADD(slot, var)
 #endif
 
 namespace ga {
@@ -89,7 +97,7 @@ tc_fwd_kernel(const TcFwdParams p)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int num_tiles = (p.M + kBM - 1) / kBM;
 #if GA_TC_TIMING
-    long long tw_[2] = {0, 0};
+    long long tw_[4] = {0, 0, 0, 0};
     const long long tstart_ = clock64();
 #endif
 
@@ -344,6 +352,22 @@ constexpr int kMnTile = 4 * kGkChunk;     // 16 KB: MN-major image [4 x 32-chann
 #ifndef GA_BWD_EWARPS
 #define GA_BWD_EWARPS 8
 #endif
+#ifndef GA_BWD_CPASYNC
+#define GA_BWD_CPASYNC 1
+#endif
+#ifndef GA_BWD_LOOK
+#define GA_BWD_LOOK 2
+#endif
+#ifndef GA_BWD_DIRECT_STORE
+#define GA_BWD_DIRECT_STORE 1
+#endif
+#ifndef GA_BWD_EARLY_EMPTY
+#define GA_BWD_EARLY_EMPTY 0
+#endif
+#ifndef GA_BWD_WT_VEC
+#define GA_BWD_WT_VEC 1
+#endif
+constexpr int kLook = GA_BWD_LOOK;               // tiles of raw operand copies in flight per producer thread (1 or 2; < kBStages)
 constexpr int kBwdEWarps = GA_BWD_EWARPS;  // epilogue warps: 4 (each 2 x 16 pixels) or 8 (two per TMEM lane quarter, 16 pixels each)
 constexpr int kBwdThreads = (17 + kBwdEWarps) * 32;      // 8 G-producer warps, 8 X-producer warps, 1 MMA warp, epilogue warps
 constexpr int kBwdMmaWarp = 16, kBwdEpiWarp0 = 17;
@@ -383,7 +407,7 @@ tc_bwd_kernel(const TcBwdParams p)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int num_tiles = (p.M + kPx - 1) / kPx;
 #if GA_TC_TIMING
-    long long tw_[2] = {0, 0};
+    long long tw_[4] = {0, 0, 0, 0};
     const long long tstart_ = clock64();
 #endif
 
@@ -397,6 +421,18 @@ tc_bwd_kernel(const TcBwdParams p)
     if (warp == kBwdMmaWarp) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
     pdl_wait();            // barrier init and TMEM allocation above overlap the previous kernel's tail
     // W^T -> shared (K-major over the OUTPUT channel): element (in, out) <- W[out][in]
+#if GA_BWD_WT_VEC
+    // thread = (input channel, group of 4 output channels): four coalesced row reads of W, ONE 16-byte store of the transposed quad
+    // (the 8 lanes of a store phase have 8 different `in & 7`, hence 8 different 16-byte units: conflict-free)
+    for (int i = tid; i < 128 * 32; i += kBwdThreads) {
+        const int in = i & 127, o = (i >> 7) * 4;
+        if (in < p.kin) {
+            const float *wp = p.W + (size_t)o * p.ldw + in;
+            const float4 v = to_tf32(make_float4(wp[0], wp[p.ldw], wp[2 * p.ldw], wp[3 * p.ldw]));
+            *reinterpret_cast<float4 *>(sm.wt + (o >> 5) * (128 * 128) + in * 128 + ((((o & 31) >> 2) ^ (in & 7)) << 4)) = v;
+        }
+    }
+#else
     const int kq = p.kin >> 2;
     for (int i = tid; i < 128 * kq; i += kBwdThreads) {
         const int o = i / kq, q = i % kq;                // W row o, input channels 4q..4q+3 (rows >= kin of W^T stay undefined:
@@ -409,6 +445,7 @@ tc_bwd_kernel(const TcBwdParams p)
             *reinterpret_cast<float *>(sm.wt + (o >> 5) * (128 * 128) + in * 128 + ((((o & 31) >> 2) ^ (in & 7)) << 4) + (o & 3) * 4) = e[t];
         }
     }
+#endif
     for (int i = tid; i < 128; i += kBwdThreads) {
         if (p.ga) {   // ga (dZ - m1 - (Y - mu) rstd m2)
             const float ga = p.ga[i], k = p.rstd[i] * p.m2[i];
@@ -428,6 +465,10 @@ tc_bwd_kernel(const TcBwdParams p)
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = sm.tmem_base;
+#if GA_TC_TIMING
+    const long long tpro_ = clock64() - tstart_;
+    long long tloop_ = 0;
+#endif
 
     // ================================ producers: warps 0-7 build G (two swizzles), warps 8-15 build X ==================
     // Both wgrad operands are consumed MN-major (pixel = K index), which for 32-bit elements means the 128-byte swizzle with a
@@ -457,29 +498,56 @@ tc_bwd_kernel(const TcBwdParams p)
             const bool has_y = p.ga != nullptr;
             const float *dz0 = p.dZ + (size_t)p0 * ldg + ch, *y0 = (has_y ? p.Y : p.dZ) + (size_t)p0 * ldg + ch;   // block e adds 8 e rows
             const size_t tile_stride = (size_t)kPx * ldg;
-            auto ldblk = [&](int t, int e, float4 &za, float4 &ya) {
-                const bool ok = t * kPx + e * 8 + p0 < M;
-                if (GA_ABLATE & 1) { za = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); ya = za; return; }
-                za = ok ? *reinterpret_cast<const float4 *>(dz0 + (size_t)t * tile_stride + (size_t)(e * 8) * ldg) : make_float4(0.f, 0.f, 0.f, 0.f);
-                ya = ok ? *reinterpret_cast<const float4 *>(y0 + (size_t)t * tile_stride + (size_t)(e * 8) * ldg) : make_float4(0.f, 0.f, 0.f, 0.f);
-            };
-            float4 va[4], vb[4];
-            if (tile < num_tiles) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) ldblk(tile, e, va[e], vb[e]);
-            }
-            for (; tile < num_tiles; tile += gstep) {
-                const int next = tile + gstep;
-                const bool has_next = next < num_tiles;
-                TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
-                unsigned char *gk = sm.gk[s] + k_off, *gm = sm.gm[s] + mn_off;
+#if GA_BWD_CPASYNC
+            // The raw dZ / Y pieces travel global -> shared with 16-byte cp.async, each straight to the address its converted value will
+            // occupy (dZ: the K-major image, Y: the MN-major image), kLook tiles ahead and without a register; once a tile has landed, the
+            // thread that copied a piece reads it back, folds the BatchNorm backward and overwrites both images IN PLACE -- every piece is
+            // private to one thread, so the conversion needs no synchronisation beyond cp.async.wait_group.
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int row8 = 8 * ldg;
+            const ptrdiff_t ydelta = y0 - dz0;
+            auto issue = [&](int t, int st) {
+                if (GA_ABLATE & 1) return;
+                const uint32_t dk = smem_u32(sm.gk[st]) + k_off, dm = smem_u32(sm.gm[st]) + mn_off;
+                const float *pz = dz0 + (size_t)t * tile_stride;
+                const bool whole = (t + 1) * kPx <= M;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
+                    const bool ok = whole || t * kPx + e * 8 + p0 < M;
+                    const float *src = ok ? pz + e * row8 : dz0;
+                    cp_async16(dk + e * 1024, src, ok);
+                    if (has_y) cp_async16(dm + e * 1024, ok ? src + ydelta : dz0, ok);
+                }
+            };
+            // Copies run up to two tiles ahead.  The stage of the tile after next is the one the epilogue frees LAST, so it is only probed:
+            // if it is still busy the copy is issued one iteration later (blocking then would serialise conversion behind the epilogue).
+            int tl = tile, sl = 0, nl = 0, ahead = 0;      // next tile to copy, its stage / round; tiles copied but not yet converted
+            auto refill = [&]() {
+                while (ahead < kLook && tl < num_tiles) {
+                    if (ahead == 0) TWAIT(0, warp_wait(&sm.empty[sl], (nl & 1) ^ 1, lane));
+                    else if (!warp_test(&sm.empty[sl], (nl & 1) ^ 1, lane)) break;
+                    issue(tl, sl);
+                    cp_async_commit();                     // one group per tile
+                    ++ahead; tl += gstep; if (++sl == kBStages) { sl = 0; ++nl; }
+                }
+            };
+            refill();
+            for (; tile < num_tiles; tile += gstep) {
+                if (ahead >= 2) cp_async_wait<1>(); else cp_async_wait<0>();      // this tile's pieces have landed (a younger group stays in flight)
+                unsigned char *gk = sm.gk[s] + k_off, *gm = sm.gm[s] + mn_off;
+                const bool ragged = (tile + 1) * kPx > M;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float4 za, ya;
+                    if (GA_ABLATE & 1) { za = ya = make_float4(0.5f, 0.25f, 0.125f, 1.f); }
+                    else {
+                        za = *reinterpret_cast<const float4 *>(gk + e * 1024);
+                        ya = has_y ? *reinterpret_cast<const float4 *>(gm + e * 1024) : za;
+                    }
                     float4 o;
-                    o.x = fmaf(cA.x, va[e].x, fmaf(cB.x, vb[e].x, cC.x)); o.y = fmaf(cA.y, va[e].y, fmaf(cB.y, vb[e].y, cC.y));
-                    o.z = fmaf(cA.z, va[e].z, fmaf(cB.z, vb[e].z, cC.z)); o.w = fmaf(cA.w, va[e].w, fmaf(cB.w, vb[e].w, cC.w));
-                    if (tile * kPx + e * 8 + p0 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_next) ldblk(next, e, va[e], vb[e]);
+                    o.x = fmaf(cA.x, za.x, fmaf(cB.x, ya.x, cC.x)); o.y = fmaf(cA.y, za.y, fmaf(cB.y, ya.y, cC.y));
+                    o.z = fmaf(cA.z, za.z, fmaf(cB.z, ya.z, cC.z)); o.w = fmaf(cA.w, za.w, fmaf(cB.w, ya.w, cC.w));
+                    if (ragged && tile * kPx + e * 8 + p0 >= M) o = zero4;       // rows >= M carry zeros (gC alone would not be zero)
                     o = to_tf32(o);
                     *reinterpret_cast<float4 *>(gk + e * 1024) = o;
                     *reinterpret_cast<float4 *>(gm + e * 1024) = o;
@@ -487,7 +555,69 @@ tc_bwd_kernel(const TcBwdParams p)
                 fence_proxy_async_smem();
                 warp_arrive(&sm.full[s], lane);
                 if (++s == kBStages) { s = 0; ++n; }
+                --ahead;
+                refill();
             }
+#else
+            // running pointers: the tile to PREFETCH (one ahead of the tile being converted); block e is 8 e rows further down.  Only the
+            // last tile can be ragged, so the row test is one uniform branch per tile instead of a predicate per load.
+            const float *pz = dz0 + (size_t)tile * tile_stride;
+            const ptrdiff_t ydelta = y0 - dz0;
+            const size_t pstep = (size_t)gstep * tile_stride;
+            const int row8 = 8 * ldg;
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 va[4], vb[4];
+            // PF: 0 = no next tile, 1 = next tile complete (plain loads), 2 = next tile ragged (row test per load)
+            auto ldblk = [&](auto pf, int t, int e) {
+                constexpr int PF = decltype(pf)::value;
+                if (PF == 0) return;
+                if (GA_ABLATE & 1) { va[e] = vb[e] = make_float4(0.5f, 0.25f, 0.125f, 1.f); return; }
+                const bool ok = PF == 1 || t * kPx + e * 8 + p0 < M;
+                va[e] = ok ? *reinterpret_cast<const float4 *>(pz + e * row8) : zero4;
+                vb[e] = ok ? *reinterpret_cast<const float4 *>(pz + ydelta + e * row8) : zero4;
+            };
+            auto fill = [&](auto pf, int next, bool ragged) {
+                unsigned char *gk = sm.gk[s] + k_off, *gm = sm.gm[s] + mn_off;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float4 o;
+                    o.x = fmaf(cA.x, va[e].x, fmaf(cB.x, vb[e].x, cC.x)); o.y = fmaf(cA.y, va[e].y, fmaf(cB.y, vb[e].y, cC.y));
+                    o.z = fmaf(cA.z, va[e].z, fmaf(cB.z, vb[e].z, cC.z)); o.w = fmaf(cA.w, va[e].w, fmaf(cB.w, vb[e].w, cC.w));
+                    if (ragged && (next - gstep) * kPx + e * 8 + p0 >= M) o = zero4;   // rows >= M carry zeros (gC alone would not be zero)
+                    ldblk(pf, next, e);                 // block e of the NEXT tile is fetched as soon as block e of this one has been consumed
+                    o = to_tf32(o);
+                    *reinterpret_cast<float4 *>(gk + e * 1024) = o;
+                    *reinterpret_cast<float4 *>(gm + e * 1024) = o;
+                }
+            };
+            using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+            if (tile < num_tiles) {
+                if ((tile + 1) * kPx <= M) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ldblk(I1{}, tile, e);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ldblk(I2{}, tile, e);
+                }
+                pz += pstep;
+            }
+            for (; tile < num_tiles; tile += gstep) {
+                const int next = tile + gstep;
+                const bool ragged = (tile + 1) * kPx > M;
+                TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
+                TMARK(tf_);
+                if (next >= num_tiles) fill(I0{}, next, ragged);
+                else if ((next + 1) * kPx <= M) fill(I1{}, next, ragged);
+                else fill(I2{}, next, ragged);
+                pz += pstep;
+                TADD(2, tf_);
+                TMARK(ta_);
+                fence_proxy_async_smem();
+                warp_arrive(&sm.full[s], lane);
+                TADD(3, ta_);
+                if (++s == kBStages) { s = 0; ++n; }
+            }
+#endif
         } else {
             const int ldp = p.ldp;
             const bool raw = p.x_raw != 0 || (GA_ABLATE & 2);
@@ -495,36 +625,106 @@ tc_bwd_kernel(const TcBwdParams p)
             const bool okc = ch < p.kin;
             const float *x0 = p.Yprev + (size_t)p0 * ldp + ch;
             const size_t tile_stride = (size_t)kPx * ldp;
-            auto ldblk = [&](int t, int e, float4 &xa) {
-                const bool ok = okc && (t * kPx + e * 8 + p0 < M);
-                if (GA_ABLATE & 1) { xa = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); return; }
-                xa = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)t * tile_stride + (size_t)(e * 8) * ldp) : make_float4(0.f, 0.f, 0.f, 0.f);
-            };
-            float4 va[4];
-            if (tile < num_tiles) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) ldblk(tile, e, va[e]);
-            }
-            for (; tile < num_tiles; tile += gstep) {
-                const int next = tile + gstep;
-                const bool has_next = next < num_tiles;
-                TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
-                unsigned char *xm = sm.xm[s] + mn_off;
+#if GA_BWD_CPASYNC
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int row8 = 8 * ldp;
+            auto issue = [&](int t, int st) {
+                if (GA_ABLATE & 1) return;
+                const uint32_t dm = smem_u32(sm.xm[st]) + mn_off;
+                const float *px = x0 + (size_t)t * tile_stride;
+                const bool whole = (t + 1) * kPx <= M;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    float4 o = va[e];
-                    if (has_next) ldblk(next, e, va[e]);
+                    const bool ok = okc && (whole || t * kPx + e * 8 + p0 < M);     // channels past kin (the 72-wide input layer) are never read
+                    cp_async16(dm + e * 1024, ok ? px + e * row8 : p.Yprev, ok);
+                }
+            };
+            int tl = tile, sl = 0, nl = 0, ahead = 0;
+            auto refill = [&]() {
+                while (ahead < kLook && tl < num_tiles) {
+                    if (ahead == 0) TWAIT(0, warp_wait(&sm.empty[sl], (nl & 1) ^ 1, lane));
+                    else if (!warp_test(&sm.empty[sl], (nl & 1) ^ 1, lane)) break;
+                    issue(tl, sl);
+                    cp_async_commit();
+                    ++ahead; tl += gstep; if (++sl == kBStages) { sl = 0; ++nl; }
+                }
+            };
+            refill();
+            for (; tile < num_tiles; tile += gstep) {
+                if (ahead >= 2) cp_async_wait<1>(); else cp_async_wait<0>();
+                unsigned char *xm = sm.xm[s] + mn_off;
+                const bool ragged = (tile + 1) * kPx > M;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float4 o = (GA_ABLATE & 1) ? make_float4(0.5f, 0.25f, 0.125f, 1.f) : *reinterpret_cast<const float4 *>(xm + e * 1024);
                     if (!raw) {
                         o.x = softplus_log2(fmaf(o.x, av.x, bv.x)); o.y = softplus_log2(fmaf(o.y, av.y, bv.y));
                         o.z = softplus_log2(fmaf(o.z, av.z, bv.z)); o.w = softplus_log2(fmaf(o.w, av.w, bv.w));
                     }
-                    if (!okc || tile * kPx + e * 8 + p0 >= M) o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!okc || (ragged && tile * kPx + e * 8 + p0 >= M)) o = zero4;      // softplus(bn(0)) is not 0: rows >= M must be
                     *reinterpret_cast<float4 *>(xm + e * 1024) = to_tf32(o);
                 }
                 fence_proxy_async_smem();
                 warp_arrive(&sm.full[s], lane);
                 if (++s == kBStages) { s = 0; ++n; }
+                --ahead;
+                refill();
             }
+#else
+            const float *px = x0 + (size_t)tile * tile_stride;
+            const size_t pstep = (size_t)gstep * tile_stride;
+            const int row8 = 8 * ldp;
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 va[4];
+            auto ldblk = [&](auto pf, int t, int e) {
+                constexpr int PF = decltype(pf)::value;
+                if (PF == 0) return;
+                if (GA_ABLATE & 1) { va[e] = make_float4(0.5f, 0.25f, 0.125f, 1.f); return; }
+                const bool ok = okc && (PF == 1 || t * kPx + e * 8 + p0 < M);      // channels past kin (the 72-wide input layer) are never read
+                va[e] = ok ? *reinterpret_cast<const float4 *>(px + e * row8) : zero4;
+            };
+            auto fill = [&](auto pf, int next, bool ragged) {
+                unsigned char *xm = sm.xm[s] + mn_off;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    float4 o = va[e];
+                    ldblk(pf, next, e);
+                    if (!raw) {
+                        o.x = softplus_log2(fmaf(o.x, av.x, bv.x)); o.y = softplus_log2(fmaf(o.y, av.y, bv.y));
+                        o.z = softplus_log2(fmaf(o.z, av.z, bv.z)); o.w = softplus_log2(fmaf(o.w, av.w, bv.w));
+                    }
+                    if (!okc || (ragged && (next - gstep) * kPx + e * 8 + p0 >= M)) o = zero4;    // softplus(bn(0)) is not 0: rows >= M must be
+                    *reinterpret_cast<float4 *>(xm + e * 1024) = to_tf32(o);
+                }
+            };
+            using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+            if (tile < num_tiles) {
+                if ((tile + 1) * kPx <= M) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ldblk(I1{}, tile, e);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ldblk(I2{}, tile, e);
+                }
+                px += pstep;
+            }
+            for (; tile < num_tiles; tile += gstep) {
+                const int next = tile + gstep;
+                const bool ragged = (tile + 1) * kPx > M;
+                TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
+                TMARK(tf_);
+                if (next >= num_tiles) fill(I0{}, next, ragged);
+                else if ((next + 1) * kPx <= M) fill(I1{}, next, ragged);
+                else fill(I2{}, next, ragged);
+                px += pstep;
+                TADD(2, tf_);
+                TMARK(ta_);
+                fence_proxy_async_smem();
+                warp_arrive(&sm.full[s], lane);
+                TADD(3, ta_);
+                if (++s == kBStages) { s = 0; ++n; }
+            }
+#endif
         }
     } else if (warp == kBwdMmaWarp) {
         // ================================ MMA issuer ================================
@@ -536,6 +736,7 @@ tc_bwd_kernel(const TcBwdParams p)
             TWAIT(0, warp_wait(&sm.full[s], n & 1, lane));
             TWAIT(1, warp_wait(&sm.tmem_empty[s], (n & 1) ^ 1, lane));
             tc_fence_after_sync();
+            TMARK(tm_);
             if (lane == 0 && (GA_ABLATE & 4)) mma_commit(&sm.mma_done[s]);
             if (lane == 0 && !(GA_ABLATE & 4)) {
                 constexpr uint32_t hi = desc_hi(1024);
@@ -556,6 +757,7 @@ tc_bwd_kernel(const TcBwdParams p)
                 mma_commit(&sm.mma_done[s]);
             }
             __syncwarp();
+            TADD(2, tm_);
             if (++s == kBStages) { s = 0; ++n; }
         }
     } else {
@@ -576,20 +778,33 @@ tc_bwd_kernel(const TcBwdParams p)
         const int ldo = p.ldo;
         double d1 = 0.0, d2 = 0.0;
         int s = 0, n = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // running pointers (advanced by one grid round of tiles): the channel column this thread accumulates into, and the rows this warp stores
+        const size_t ostep = (size_t)gridDim.x * kPx * ldo;
+        const float *evp = p.dZprev + (size_t)blockIdx.x * kPx * ldo + c;
+        float *outp = p.dZprev + ((size_t)blockIdx.x * kPx + ew * kStoreRows) * ldo + lane * 4;
+        const bool store_lane = lane * 4 < p.kin && !(GA_ABLATE & 16);
+        const bool store_col = c < p.kin && !(GA_ABLATE & 16);
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, evp += ostep, outp += ostep) {
             const int m0 = tile * kPx;
+            const bool full = m0 + kPx <= p.M;            // only the last tile can be ragged: one uniform branch instead of a test per row
             // raw dX already accumulated by an earlier layer of this fan-in: fetched BEFORE waiting for the tensor core, and the second
             // half while the first is being processed, so the latency hides behind the MMA and the sigmoid math (rows >= M are never read)
             float ev[16];
             auto ldev = [&](int ph) {
-                const float *ep = p.dZprev + (size_t)(m0 + ph * 16) * ldo + c;
-                const int rows = p.M - (m0 + ph * 16);
+                const float *ep = evp + ph * 16 * ldo;
+                if (full) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) ev[j] = (j < rows) ? ep[(size_t)j * ldo] : 0.f;
+                    for (int j = 0; j < 16; ++j) ev[j] = ep[j * ldo];
+                } else {
+                    const int rows = p.M - (m0 + ph * 16);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) ev[j] = (j < rows) ? ep[j * ldo] : 0.f;
+                }
             };
             if (add_existing) ldev(ew >> 2);
             TWAIT(0, warp_wait(&sm.mma_done[s], n & 1, lane));
             tc_fence_after_sync();
+            TMARK(te_);
             float *stg = reinterpret_cast<float *>(sm.gk[s]) + c;      // both products have consumed this stage: [32 px][128] staging
             float t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
@@ -617,23 +832,63 @@ tc_bwd_kernel(const TcBwdParams p)
                         t2 = fmaf(dx, fmaf(ls, cl2g, fmaf(x, cinvg, -cbg)), t2);
                     }
                 }
+#if GA_BWD_DIRECT_STORE
+                // straight from the registers: a warp instruction writes 32 consecutive channels of one pixel = one whole 128-byte line
+                if (store_col) {
+                    float *oc = const_cast<float *>(evp) + ph * 16 * ldo;
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) oc[j * ldo] = v[j];
+                    } else {
+                        const int rows = p.M - (m0 + ph * 16);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) if (j < rows) oc[j * ldo] = v[j];
+                    }
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < 16; ++j) stg[(ph * 16 + j) * 128] = v[j];
+#endif
             }
             tc_fence_before_sync();
             warp_arrive(&sm.tmem_empty[s], lane);
             d1 += (double)t1; d2 += (double)t2;
+            TADD(2, te_);
+#if GA_BWD_DIRECT_STORE
+            TMARK(ts_);
+            warp_arrive(&sm.empty[s], lane);               // the X tile has been read: nothing of this stage is needed any more
+#elif GA_BWD_EARLY_EMPTY
             TWAIT(1, named_bar_sync(1, kBwdEWarps * 32));
+            TMARK(ts_);
+            {   // rows to registers, stage handed back, THEN the global stores: the producers do not wait behind the store issue
+                float4 rowv[kStoreRows];
+                const float *srow = reinterpret_cast<const float *>(sm.gk[s]) + (ew * kStoreRows) * 128 + lane * 4;
 #pragma unroll
-            for (int r = ew * kStoreRows; r < ew * kStoreRows + kStoreRows; ++r) {
-                const int m = m0 + r;
-                if (m >= p.M) break;
-                if (lane * 4 < p.kin && !(GA_ABLATE & 16))
-                    *reinterpret_cast<float4 *>(p.dZprev + (size_t)m * p.ldo + lane * 4) = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(sm.gk[s]) + r * 128 + lane * 4);
+                for (int r = 0; r < kStoreRows; ++r) rowv[r] = *reinterpret_cast<const float4 *>(srow + r * 128);
+                warp_arrive(&sm.empty[s], lane);
+                if (store_lane) {
+#pragma unroll
+                    for (int r = 0; r < kStoreRows; ++r)
+                        if (full || m0 + ew * kStoreRows + r < p.M) *reinterpret_cast<float4 *>(outp + r * ldo) = rowv[r];
+                }
+            }
+#else
+            TWAIT(1, named_bar_sync(1, kBwdEWarps * 32));
+            TMARK(ts_);
+            if (store_lane) {
+                const float *srow = reinterpret_cast<const float *>(sm.gk[s]) + (ew * kStoreRows) * 128 + lane * 4;
+#pragma unroll
+                for (int r = 0; r < kStoreRows; ++r)
+                    if (full || m0 + ew * kStoreRows + r < p.M) *reinterpret_cast<float4 *>(outp + r * ldo) = *reinterpret_cast<const float4 *>(srow + r * 128);
             }
             warp_arrive(&sm.empty[s], lane);
+#endif
+            TADD(3, ts_);
             if (++s == kBStages) { s = 0; ++n; }
         }
+#if GA_TC_TIMING
+        tloop_ = clock64() - tstart_;
+#endif
         if (final_mode && p.s1) { atomicAdd(&p.s1[c], d1); atomicAdd(&p.s2[c], d2); }
         // flush the weight-gradient accumulator: lane == output channel; every MMA was covered by the last mma_done wait
         tc_fence_after_sync();
@@ -647,7 +902,7 @@ tc_bwd_kernel(const TcBwdParams p)
         }
     }
 #if GA_TC_TIMING
-    if (blockIdx.x == 0 && lane == 0) printf("TCT bwd mode=%d kin=%d warp %d total %lld wait0 %lld wait1 %lld tiles %d\n", p.mode, p.kin, warp, clock64() - tstart_, tw_[0], tw_[1], (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x);
+    if (blockIdx.x == 0 && lane == 0) printf("TCT bwd pro %lld loopend %lld mode=%d kin=%d warp %d total %lld wait0 %lld wait1 %lld ph2 %lld ph3 %lld tiles %d\n", tpro_, tloop_, p.mode, p.kin, warp, clock64() - tstart_, tw_[0], tw_[1], tw_[2], tw_[3], (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x);
 #endif
     tc_fence_before_sync();
     __syncthreads();

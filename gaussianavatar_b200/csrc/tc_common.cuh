@@ -58,6 +58,21 @@ __device__ __forceinline__ void warp_arrive(uint64_t *bar, int lane)
     if (lane == 0) mbar_arrive(bar);
 }
 #endif
+// Non-blocking probe of a phase (warp-uniform result): lane 0 tests, the answer is broadcast.
+__device__ __forceinline__ bool warp_test(uint64_t *bar, uint32_t parity, int lane)
+{
+    uint32_t ok = 0;
+    if (lane == 0)
+        asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+// 16-byte asynchronous global -> shared copy (L2 only); !valid: the 16 bytes are zero-filled and nothing is read
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16u : 0u) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
