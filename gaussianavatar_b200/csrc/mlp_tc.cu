@@ -337,9 +337,17 @@ extern "C" int ga_tc_linear_forward(int32_t M, int32_t K, const float *X, int32_
 //                               TRANSPOSED so that a TMEM lane is an input channel: the epilogue thread's BatchNorm
 //                               scalars are constants and sum(dZ), sum(dZ xhat) need no cross-thread reduction
 //   dZ_{l-1} = dX * sigmoid(z_{l-1})   (sigmoid(z_{l-1}) and xhat_{l-1} recovered from x = softplus(z) in the X tile: no re-read)
-// G is stored in two swizzles of the same [px][channel] image (K-major operands reject layout type 1), X once; every store
-// is a conflict-free STS.128 of a full 128-byte row and every global load a full line.  32-pixel tiles, three stages,
-// 25 warps: 8 producers for G, 8 for X, 1 MMA issuer, 8 epilogue (two per TMEM lane quarter, 16 pixels each).
+// G is stored in two swizzles of the same [px][channel] image (K-major operands reject layout type 1), X once.  The raw operands
+// travel global -> shared with 16-byte cp.async (no register behind a load in flight) and are converted IN PLACE; dZ_{l-1} leaves
+// straight from the epilogue registers (one whole 128-byte line per warp instruction).  32-pixel tiles, three stages, 25 warps:
+// 8 converters for G, 8 for X, 1 MMA issuer, 8 epilogue (two per TMEM lane quarter, 16 pixels each).
+// Round-2 log (tools/variants.py on the device, profiles/r2_tc_bwd_ncu.md): register loads one tile ahead -> cp.async in place
+// 1.97 -> 1.63 ms per step; shared-memory staging + named barrier + row stores -> direct stores 1.63 -> 1.55 ms.  What did NOT pay:
+// bulk L2 prefetch from the MMA warp (3.1 ms: 128 small TMA requests per tile), dedicated copy warps / copies issued by the
+// epilogue warps with mbarrier completion (1.8 / 1.7 ms: one more parked wait per tile on the ring), spinning instead of
+// suspended mbarrier waits (1.8 ms), "arrive before prefetch" (2.0 ms).  With every load, store, MMA and activation ablated the
+// skeleton (waits, converter LDS/STS, tcgen05.ld) still takes 58 us of the 129 us per launch: the kernel is bound by the per-tile
+// hand-offs of its 32-pixel tiles, which the 227 KB of shared memory do not allow to grow (64 KB W^T + 3 x 48 KB stages).
 // =====================================================================================================================
 namespace ga {
 namespace {
@@ -352,20 +360,8 @@ constexpr int kMnTile = 4 * kGkChunk;     // 16 KB: MN-major image [4 x 32-chann
 #ifndef GA_BWD_EWARPS
 #define GA_BWD_EWARPS 8
 #endif
-#ifndef GA_BWD_CPASYNC
-#define GA_BWD_CPASYNC 1
-#endif
 #ifndef GA_BWD_LOOK
 #define GA_BWD_LOOK 2
-#endif
-#ifndef GA_BWD_DIRECT_STORE
-#define GA_BWD_DIRECT_STORE 1
-#endif
-#ifndef GA_BWD_EARLY_EMPTY
-#define GA_BWD_EARLY_EMPTY 0
-#endif
-#ifndef GA_BWD_WT_VEC
-#define GA_BWD_WT_VEC 1
 #endif
 constexpr int kLook = GA_BWD_LOOK;               // tiles of raw operand copies in flight per producer thread (1 or 2; < kBStages)
 constexpr int kBwdEWarps = GA_BWD_EWARPS;  // epilogue warps: 4 (each 2 x 16 pixels) or 8 (two per TMEM lane quarter, 16 pixels each)
@@ -421,7 +417,6 @@ tc_bwd_kernel(const TcBwdParams p)
     if (warp == kBwdMmaWarp) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
     pdl_wait();            // barrier init and TMEM allocation above overlap the previous kernel's tail
     // W^T -> shared (K-major over the OUTPUT channel): element (in, out) <- W[out][in]
-#if GA_BWD_WT_VEC
     // thread = (input channel, group of 4 output channels): four coalesced row reads of W, ONE 16-byte store of the transposed quad
     // (the 8 lanes of a store phase have 8 different `in & 7`, hence 8 different 16-byte units: conflict-free)
     for (int i = tid; i < 128 * 32; i += kBwdThreads) {
@@ -432,20 +427,6 @@ tc_bwd_kernel(const TcBwdParams p)
             *reinterpret_cast<float4 *>(sm.wt + (o >> 5) * (128 * 128) + in * 128 + ((((o & 31) >> 2) ^ (in & 7)) << 4)) = v;
         }
     }
-#else
-    const int kq = p.kin >> 2;
-    for (int i = tid; i < 128 * kq; i += kBwdThreads) {
-        const int o = i / kq, q = i % kq;                // W row o, input channels 4q..4q+3 (rows >= kin of W^T stay undefined:
-                                                         // they only feed accumulator rows / columns that are never stored)
-        const float4 v = to_tf32(*reinterpret_cast<const float4 *>(p.W + (size_t)o * p.ldw + q * 4));
-        const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int in = q * 4 + t;
-            *reinterpret_cast<float *>(sm.wt + (o >> 5) * (128 * 128) + in * 128 + ((((o & 31) >> 2) ^ (in & 7)) << 4) + (o & 3) * 4) = e[t];
-        }
-    }
-#endif
     for (int i = tid; i < 128; i += kBwdThreads) {
         if (p.ga) {   // ga (dZ - m1 - (Y - mu) rstd m2)
             const float ga = p.ga[i], k = p.rstd[i] * p.m2[i];
@@ -470,16 +451,14 @@ tc_bwd_kernel(const TcBwdParams p)
     long long tloop_ = 0;
 #endif
 
-    // ================================ producers: warps 0-7 build G (two swizzles), warps 8-15 build X ==================
+    // ================================ converters: warps 0-7 build G (two swizzles), warps 8-15 build X =================
     // Both wgrad operands are consumed MN-major (pixel = K index), which for 32-bit elements means the 128-byte swizzle with a
     // 32-byte base (layout type 1; the physical layout was decoded with tools/exp_umma_probe.cu):
     //     byte(px, c) = (c / 32) * LBO + (px / 4) * SBO + (px % 4) * 128 + ((((c % 32) / 8) ^ (px % 4)) * 32) + (c % 8) * 4
     // so a pixel's 32 channels stay one permuted 128-byte row, exactly like the K-major image the dgrad needs (16-byte units
-    // XOR px % 8).  A warp instruction therefore covers 4 pixels x 128 B: full-line global loads, and every quarter-warp
-    // stores one whole row -> both images are written with conflict-free STS.128, no transposition anywhere.
-    // Warp w owns the 32-channel chunk j = w & 3 (its BatchNorm coefficients are thread constants) and pixel groups
-    // (w >> 2) + 2 e, e = 0..3.  Loads are software-pipelined (block e of the NEXT tile is fetched as soon as block e of the
-    // current one has been consumed) and every offset is a thread constant plus a compile-time term.
+    // XOR px % 8): the two images differ only by a permutation of the 16-byte pieces inside each 128-byte row.  A warp instruction
+    // covers 4 pixels x 128 B (full-line global requests) and every quarter-warp touches one whole row (conflict-free).
+    // Warp w owns the 32-channel chunk j = w & 3 (its BatchNorm coefficients are thread constants) and pixel rows p0 + 8 e.
     const int M = p.M;
     if (warp < kBwdMmaWarp) {
         const int c16 = lane & 7, pxl = lane >> 3;
@@ -498,7 +477,6 @@ tc_bwd_kernel(const TcBwdParams p)
             const bool has_y = p.ga != nullptr;
             const float *dz0 = p.dZ + (size_t)p0 * ldg + ch, *y0 = (has_y ? p.Y : p.dZ) + (size_t)p0 * ldg + ch;   // block e adds 8 e rows
             const size_t tile_stride = (size_t)kPx * ldg;
-#if GA_BWD_CPASYNC
             // The raw dZ / Y pieces travel global -> shared with 16-byte cp.async, each straight to the address its converted value will
             // occupy (dZ: the K-major image, Y: the MN-major image), kLook tiles ahead and without a register; once a tile has landed, the
             // thread that copied a piece reads it back, folds the BatchNorm backward and overwrites both images IN PLACE -- every piece is
@@ -558,66 +536,6 @@ tc_bwd_kernel(const TcBwdParams p)
                 --ahead;
                 refill();
             }
-#else
-            // running pointers: the tile to PREFETCH (one ahead of the tile being converted); block e is 8 e rows further down.  Only the
-            // last tile can be ragged, so the row test is one uniform branch per tile instead of a predicate per load.
-            const float *pz = dz0 + (size_t)tile * tile_stride;
-            const ptrdiff_t ydelta = y0 - dz0;
-            const size_t pstep = (size_t)gstep * tile_stride;
-            const int row8 = 8 * ldg;
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 va[4], vb[4];
-            // PF: 0 = no next tile, 1 = next tile complete (plain loads), 2 = next tile ragged (row test per load)
-            auto ldblk = [&](auto pf, int t, int e) {
-                constexpr int PF = decltype(pf)::value;
-                if (PF == 0) return;
-                if (GA_ABLATE & 1) { va[e] = vb[e] = make_float4(0.5f, 0.25f, 0.125f, 1.f); return; }
-                const bool ok = PF == 1 || t * kPx + e * 8 + p0 < M;
-                va[e] = ok ? *reinterpret_cast<const float4 *>(pz + e * row8) : zero4;
-                vb[e] = ok ? *reinterpret_cast<const float4 *>(pz + ydelta + e * row8) : zero4;
-            };
-            auto fill = [&](auto pf, int next, bool ragged) {
-                unsigned char *gk = sm.gk[s] + k_off, *gm = sm.gm[s] + mn_off;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float4 o;
-                    o.x = fmaf(cA.x, va[e].x, fmaf(cB.x, vb[e].x, cC.x)); o.y = fmaf(cA.y, va[e].y, fmaf(cB.y, vb[e].y, cC.y));
-                    o.z = fmaf(cA.z, va[e].z, fmaf(cB.z, vb[e].z, cC.z)); o.w = fmaf(cA.w, va[e].w, fmaf(cB.w, vb[e].w, cC.w));
-                    if (ragged && (next - gstep) * kPx + e * 8 + p0 >= M) o = zero4;   // rows >= M carry zeros (gC alone would not be zero)
-                    ldblk(pf, next, e);                 // block e of the NEXT tile is fetched as soon as block e of this one has been consumed
-                    o = to_tf32(o);
-                    *reinterpret_cast<float4 *>(gk + e * 1024) = o;
-                    *reinterpret_cast<float4 *>(gm + e * 1024) = o;
-                }
-            };
-            using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
-            if (tile < num_tiles) {
-                if ((tile + 1) * kPx <= M) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) ldblk(I1{}, tile, e);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) ldblk(I2{}, tile, e);
-                }
-                pz += pstep;
-            }
-            for (; tile < num_tiles; tile += gstep) {
-                const int next = tile + gstep;
-                const bool ragged = (tile + 1) * kPx > M;
-                TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
-                TMARK(tf_);
-                if (next >= num_tiles) fill(I0{}, next, ragged);
-                else if ((next + 1) * kPx <= M) fill(I1{}, next, ragged);
-                else fill(I2{}, next, ragged);
-                pz += pstep;
-                TADD(2, tf_);
-                TMARK(ta_);
-                fence_proxy_async_smem();
-                warp_arrive(&sm.full[s], lane);
-                TADD(3, ta_);
-                if (++s == kBStages) { s = 0; ++n; }
-            }
-#endif
         } else {
             const int ldp = p.ldp;
             const bool raw = p.x_raw != 0 || (GA_ABLATE & 2);
@@ -625,7 +543,6 @@ tc_bwd_kernel(const TcBwdParams p)
             const bool okc = ch < p.kin;
             const float *x0 = p.Yprev + (size_t)p0 * ldp + ch;
             const size_t tile_stride = (size_t)kPx * ldp;
-#if GA_BWD_CPASYNC
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const int row8 = 8 * ldp;
             auto issue = [&](int t, int st) {
@@ -670,61 +587,6 @@ tc_bwd_kernel(const TcBwdParams p)
                 --ahead;
                 refill();
             }
-#else
-            const float *px = x0 + (size_t)tile * tile_stride;
-            const size_t pstep = (size_t)gstep * tile_stride;
-            const int row8 = 8 * ldp;
-            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 va[4];
-            auto ldblk = [&](auto pf, int t, int e) {
-                constexpr int PF = decltype(pf)::value;
-                if (PF == 0) return;
-                if (GA_ABLATE & 1) { va[e] = make_float4(0.5f, 0.25f, 0.125f, 1.f); return; }
-                const bool ok = okc && (PF == 1 || t * kPx + e * 8 + p0 < M);      // channels past kin (the 72-wide input layer) are never read
-                va[e] = ok ? *reinterpret_cast<const float4 *>(px + e * row8) : zero4;
-            };
-            auto fill = [&](auto pf, int next, bool ragged) {
-                unsigned char *xm = sm.xm[s] + mn_off;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float4 o = va[e];
-                    ldblk(pf, next, e);
-                    if (!raw) {
-                        o.x = softplus_log2(fmaf(o.x, av.x, bv.x)); o.y = softplus_log2(fmaf(o.y, av.y, bv.y));
-                        o.z = softplus_log2(fmaf(o.z, av.z, bv.z)); o.w = softplus_log2(fmaf(o.w, av.w, bv.w));
-                    }
-                    if (!okc || (ragged && (next - gstep) * kPx + e * 8 + p0 >= M)) o = zero4;    // softplus(bn(0)) is not 0: rows >= M must be
-                    *reinterpret_cast<float4 *>(xm + e * 1024) = to_tf32(o);
-                }
-            };
-            using I0 = std::integral_constant<int, 0>; using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
-            if (tile < num_tiles) {
-                if ((tile + 1) * kPx <= M) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) ldblk(I1{}, tile, e);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) ldblk(I2{}, tile, e);
-                }
-                px += pstep;
-            }
-            for (; tile < num_tiles; tile += gstep) {
-                const int next = tile + gstep;
-                const bool ragged = (tile + 1) * kPx > M;
-                TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
-                TMARK(tf_);
-                if (next >= num_tiles) fill(I0{}, next, ragged);
-                else if ((next + 1) * kPx <= M) fill(I1{}, next, ragged);
-                else fill(I2{}, next, ragged);
-                px += pstep;
-                TADD(2, tf_);
-                TMARK(ta_);
-                fence_proxy_async_smem();
-                warp_arrive(&sm.full[s], lane);
-                TADD(3, ta_);
-                if (++s == kBStages) { s = 0; ++n; }
-            }
-#endif
         }
     } else if (warp == kBwdMmaWarp) {
         // ================================ MMA issuer ================================
@@ -765,7 +627,7 @@ tc_bwd_kernel(const TcBwdParams p)
         // 4 warps (TMEM lane quarter = warp & 3).  A thread's BatchNorm scalars are constants; sigmoid(z_{l-1}) and
         // xhat_{l-1} are recovered from x = softplus(z) in the X^T tile (no global re-read); 2 x 16 pixels per tile.
         const int ew = warp - kBwdEpiWarp0;          // 0..kBwdEWarps-1
-        constexpr int kPhStep = kBwdEWarps / 4, kStoreRows = kPx / kBwdEWarps;
+        constexpr int kPhStep = kBwdEWarps / 4;
         const int q = warp & 3;
         const int c = q * 32 + lane;                 // TMEM lane == input channel
         // xhat = (z - beta) / gamma with z = x + ln2 * log2(sigmoid):  xhat = ln2/gamma * ls + (x / gamma - beta / gamma)
@@ -781,10 +643,8 @@ tc_bwd_kernel(const TcBwdParams p)
         // running pointers (advanced by one grid round of tiles): the channel column this thread accumulates into, and the rows this warp stores
         const size_t ostep = (size_t)gridDim.x * kPx * ldo;
         const float *evp = p.dZprev + (size_t)blockIdx.x * kPx * ldo + c;
-        float *outp = p.dZprev + ((size_t)blockIdx.x * kPx + ew * kStoreRows) * ldo + lane * 4;
-        const bool store_lane = lane * 4 < p.kin && !(GA_ABLATE & 16);
         const bool store_col = c < p.kin && !(GA_ABLATE & 16);
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, evp += ostep, outp += ostep) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, evp += ostep) {
             const int m0 = tile * kPx;
             const bool full = m0 + kPx <= p.M;            // only the last tile can be ragged: one uniform branch instead of a test per row
             // raw dX already accumulated by an earlier layer of this fan-in: fetched BEFORE waiting for the tensor core, and the second
@@ -805,7 +665,6 @@ tc_bwd_kernel(const TcBwdParams p)
             TWAIT(0, warp_wait(&sm.mma_done[s], n & 1, lane));
             tc_fence_after_sync();
             TMARK(te_);
-            float *stg = reinterpret_cast<float *>(sm.gk[s]) + c;      // both products have consumed this stage: [32 px][128] staging
             float t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
             for (int ph = ew >> 2; ph < 2; ph += kPhStep) {
@@ -832,7 +691,6 @@ tc_bwd_kernel(const TcBwdParams p)
                         t2 = fmaf(dx, fmaf(ls, cl2g, fmaf(x, cinvg, -cbg)), t2);
                     }
                 }
-#if GA_BWD_DIRECT_STORE
                 // straight from the registers: a warp instruction writes 32 consecutive channels of one pixel = one whole 128-byte line
                 if (store_col) {
                     float *oc = const_cast<float *>(evp) + ph * 16 * ldo;
@@ -845,44 +703,13 @@ tc_bwd_kernel(const TcBwdParams p)
                         for (int j = 0; j < 16; ++j) if (j < rows) oc[j * ldo] = v[j];
                     }
                 }
-#else
-#pragma unroll
-                for (int j = 0; j < 16; ++j) stg[(ph * 16 + j) * 128] = v[j];
-#endif
             }
             tc_fence_before_sync();
             warp_arrive(&sm.tmem_empty[s], lane);
             d1 += (double)t1; d2 += (double)t2;
             TADD(2, te_);
-#if GA_BWD_DIRECT_STORE
             TMARK(ts_);
             warp_arrive(&sm.empty[s], lane);               // the X tile has been read: nothing of this stage is needed any more
-#elif GA_BWD_EARLY_EMPTY
-            TWAIT(1, named_bar_sync(1, kBwdEWarps * 32));
-            TMARK(ts_);
-            {   // rows to registers, stage handed back, THEN the global stores: the producers do not wait behind the store issue
-                float4 rowv[kStoreRows];
-                const float *srow = reinterpret_cast<const float *>(sm.gk[s]) + (ew * kStoreRows) * 128 + lane * 4;
-#pragma unroll
-                for (int r = 0; r < kStoreRows; ++r) rowv[r] = *reinterpret_cast<const float4 *>(srow + r * 128);
-                warp_arrive(&sm.empty[s], lane);
-                if (store_lane) {
-#pragma unroll
-                    for (int r = 0; r < kStoreRows; ++r)
-                        if (full || m0 + ew * kStoreRows + r < p.M) *reinterpret_cast<float4 *>(outp + r * ldo) = rowv[r];
-                }
-            }
-#else
-            TWAIT(1, named_bar_sync(1, kBwdEWarps * 32));
-            TMARK(ts_);
-            if (store_lane) {
-                const float *srow = reinterpret_cast<const float *>(sm.gk[s]) + (ew * kStoreRows) * 128 + lane * 4;
-#pragma unroll
-                for (int r = 0; r < kStoreRows; ++r)
-                    if (full || m0 + ew * kStoreRows + r < p.M) *reinterpret_cast<float4 *>(outp + r * ldo) = *reinterpret_cast<const float4 *>(srow + r * 128);
-            }
-            warp_arrive(&sm.empty[s], lane);
-#endif
             TADD(3, ts_);
             if (++s == kBStages) { s = 0; ++n; }
         }

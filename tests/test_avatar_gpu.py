@@ -255,9 +255,12 @@ def test_inference_model_caches_the_frame_invariant_decoder_output():
         n1 = list(m.net._states.values())[0].num_batches_tracked
         assert n1 == n0 + 1, (n0, n1)          # evaluated once for the three frames
     for a, b in zip(got, ref):          # the re-evaluated net differs by the summation order of its BatchNorm statistics (double atomics):
-        d = (a - b).abs()               # round-off everywhere, at most an isolated pixel where a 1/255 or 1e-4 threshold flips
-        assert d.mean().item() < 1e-6, d.mean().item()
-        assert (d > 1e-3).float().mean().item() < 1e-4, ((d > 1e-3).sum().item(), d.max().item())
+        d = (a - b).abs()               # round-off everywhere, except where that round-off flips a rasterizer threshold (alpha < 1/255, the
+        # 3-sigma tile rectangle, T < 1e-4): a flipped Gaussian changes a handful of pixels by at most its own cut-off contribution (~1e-2).
+        # The order of the atomics differs from run to run, so the bounds must hold for a few flips, not for none.
+        assert torch.quantile(d.flatten(), 0.999).item() < 1e-4, torch.quantile(d.flatten(), 0.999).item()
+        assert d.max().item() < 5e-2, d.max().item()
+        assert d.mean().item() < 2e-5, d.mean().item()
     assert (got[0] - got[1]).abs().mean().item() > 1e-4, (got[0] - got[1]).abs().mean().item()
 
 
