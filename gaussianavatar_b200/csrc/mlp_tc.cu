@@ -1,20 +1,19 @@
 // Decoder-MLP layers on the 5th-generation tensor cores (tcgen05, kind::tf32, accumulators in TMEM).
 //
-// One persistent, warp-specialised CTA per SM computes  Y[M,128] (+)= act(bn(X))[M,K] * W[128,K]^T + bias  for its share
-// of 128-pixel tiles (17 warps):
-//   warps 0-7   producers : 16 coalesced LDG.128 per thread in flight for the raw (pre-BatchNorm) input tile, BatchNorm +
-//                           Softplus applied in registers (log2 domain), STS.128 into the 128-byte-swizzled K-major UMMA
-//                           layout, fence.proxy.async, mbarrier
-//   warp  8     MMA issuer: one elected lane issues K/8 tcgen05.mma (M=128, N=128, K=8) per tile into one of two TMEM
-//                           accumulators, tcgen05.commit -> mbarrier
-//   warps 9-16  epilogue  : two warps per TMEM lane quarter, half the channels each: tcgen05.ld (lane = pixel row), stage the
-//                           tile in the just-consumed input buffer (XOR-swizzled, conflict-free both ways), then one
-//                           coalesced 512-byte row per warp instruction: + bias, global store, and the layer's BatchNorm
-//                           sum / sum-of-squares accumulated in the same loop (float4 per lane per tile, double across
-//                           tiles, combined through shared memory: 2 atomics per channel per CTA)
-// Two input stages + two accumulators overlap load/transform, MMA and store.  The layer moves 64 KB in + 64 KB out per
-// 4.2 MFLOP tile: the tensor core takes the math off the critical path, what is left is latency / issue bound
-// (profiles/r1_tc_fwd_ncu.md), which is why the warp counts per role were tuned on the device (tools/variants.py).
+// Forward: one persistent, warp-specialised CTA per SM computes  Y[M,128] (+)= act(bn(X))[M,K] * W[128,K]^T + bias  for its share
+// of 64-pixel tiles, as the TRANSPOSED product  Y^T[out, px] = W[out, K] * act(bn(X))[px, K]^T  (17 warps):
+//   warps 0-7   converters: the raw (pre-BatchNorm) input rows travel global -> shared with 16-byte cp.async, each piece straight to
+//                           its place in the 128-byte-swizzled K-major UMMA image, up to three tiles ahead (four 32 KB stages); the thread
+//                           that copied a piece converts it IN PLACE (BatchNorm + Softplus in the log2 domain, TF32 rounding), then
+//                           fence.proxy.async, mbarrier
+//   warp  8     MMA issuer: one elected lane issues K/8 tcgen05.mma (M = 128 output channels, N = 64 pixels, K = 8) per tile into one of
+//                           four 64-column TMEM accumulators, tcgen05.commit -> mbarrier (which also frees the input stage)
+//   warps 9-16  epilogue  : two warps per TMEM lane quarter, 32 pixels each; a TMEM lane is an OUTPUT CHANNEL, so bias and the layer's
+//                           BatchNorm sum / sum-of-squares are thread-local, and Y leaves straight from the registers: a warp
+//                           instruction writes 32 channels of one pixel = one whole 128-byte line (no staging pass, no named barrier)
+// The layer moves 1 KiB per pixel against 32.8 kFLOP: HBM is the bound.  Round 1 computed Y (not Y^T) in 128-pixel tiles with two
+// 64 KB stages, register loads and a shared-memory staging pass for coalesced row stores: 0.57 of the HBM peak; this form 0.69
+// (0.863 -> 0.714 ms per step at config 3; lookahead 1 / 2 / 3 tiles: 0.93 / 0.73 / 0.71 ms).
 //
 // TF32 is what the reference computes these 1x1 convolutions in on any Ampere+ GPU (cuDNN allow_tf32 default,
 // SURVEY.md §8 a-4); the strict-FP32 CUDA-core path (gemm.cuh) remains selectable and is the GPU-side reference.
@@ -53,18 +52,6 @@ constexpr int kBM = 128, kBN = 128;
 constexpr int kChunkBytes = kBM * 128;          // one 32-channel chunk of a 128-row tile: 16 KB
 constexpr int kMaxChunks = 4;                    // K <= 128
 constexpr int kStageBytes = kMaxChunks * kChunkBytes;   // 64 KB
-#ifndef GA_FWD_PWARPS
-#define GA_FWD_PWARPS 8
-#endif
-constexpr int kFwdPWarps = GA_FWD_PWARPS;                 // producer warps: 8, or 16 = two groups of 8 that take alternate tiles (group g owns stage g)
-constexpr int kFwdGroups = kFwdPWarps / 8;
-constexpr int kFwdRowsPerThread = 16;                    // float4 loads per producer thread per tile
-#ifndef GA_FWD_EWARPS
-#define GA_FWD_EWARPS 8
-#endif
-constexpr int kFwdEWarps = GA_FWD_EWARPS;                 // epilogue warps (4, or 8: two per TMEM lane quarter, half the channels each)
-constexpr int kTcThreads = (kFwdPWarps + 1 + kFwdEWarps) * 32;
-constexpr int kFwdMmaWarp = kFwdPWarps, kFwdEpiWarp0 = kFwdPWarps + 1;
 constexpr uint32_t kTmemCols = 256;
 
 struct TcFwdParams {
@@ -77,46 +64,53 @@ struct TcFwdParams {
     int M;
 };
 
-struct alignas(1024) TcFwdSmem {
-    unsigned char w[kStageBytes];
-    unsigned char a[2][kStageBytes];
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Forward layer (see the file header).  Operand images: A = W [4 chunks][128 out rows][128 B], B = the X tile [4 chunks][64 px rows]
+// [128 B], both K-major with the 128-byte swizzle (16-byte units XOR row % 8); a chunk is 32 input channels.
+constexpr int kTPx = 64, kTStages = 4;
+constexpr int kTChunk = kTPx * 128;                 // 8 KB: [64 px rows][32 channels]
+constexpr int kTStageBytes = kMaxChunks * kTChunk;   // 32 KB
+constexpr int kTThreads = 17 * 32;
+constexpr int kTMmaWarp = 8, kTEpiWarp0 = 9;
+#ifndef GA_FWDT_LOOK
+#define GA_FWDT_LOOK 3
+#endif
+constexpr int kTLook = GA_FWDT_LOOK;                 // tiles of copies in flight per converter thread (1..3)
+
+struct alignas(1024) TcFwdTSmem {
+    unsigned char w[kStageBytes];                    // W: [4 chunks][128 out rows][128 B], K-major, 128-byte swizzle
+    unsigned char x[kTStages][kTStageBytes];         // X tile: [4 chunks][64 px rows][128 B]
     float sa[kBN], sb[kBN], sbias[kBN];
-    uint64_t full[2], empty[2], mma_done[2], tmem_empty[2];
+    double red[2][kBN];
+    uint64_t full[kTStages], mma_done[kTStages], tmem_empty[kTStages];
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
-
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTThreads, 1)
 tc_fwd_kernel(const TcFwdParams p)
 {
     extern __shared__ unsigned char smem_raw[];
-    // SWIZZLE_128B operands need 1024-byte aligned tiles: skip to the next 1 KB boundary (1 KB of slack is requested).
-    // Pointer arithmetic on the extern array keeps the shared address space visible to the compiler (LDS/STS, not LD/ST).
-    TcFwdSmem &sm = *reinterpret_cast<TcFwdSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
+    TcFwdTSmem &sm = *reinterpret_cast<TcFwdTSmem *>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int num_tiles = (p.M + kBM - 1) / kBM;
-#if GA_TC_TIMING
-    long long tw_[4] = {0, 0, 0, 0};
-    const long long tstart_ = clock64();
-#endif
+    const int num_tiles = (p.M + kTPx - 1) / kTPx;
+    const int gstep = gridDim.x;
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm.full[s], 8 * kArrivalsPerWarp); mbar_init(&sm.empty[s], kFwdEWarps * kArrivalsPerWarp);         // arrivals are per WARP (warp_arrive)
-            mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], kFwdEWarps * kArrivalsPerWarp);
+        for (int s = 0; s < kTStages; ++s) {
+            mbar_init(&sm.full[s], 8 * kArrivalsPerWarp); mbar_init(&sm.mma_done[s], 1); mbar_init(&sm.tmem_empty[s], 8 * kArrivalsPerWarp);
         }
         fence_barrier_init();
     }
-    if (warp == kFwdMmaWarp) tmem_alloc(&sm.tmem_base, kTmemCols);
-    pdl_wait();            // everything above touches only this CTA's shared / tensor memory: it overlaps the previous kernel's tail
-    // weights -> shared, K-major, 128-byte swizzle
-    for (int i = tid; i < kBN * (p.K / 4); i += kTcThreads) {
+    if (warp == kTMmaWarp) tmem_alloc(&sm.tmem_base, kTmemCols);
+    pdl_wait();
+    for (int i = tid; i < kBN * (p.K / 4); i += kTThreads) {          // weights -> shared, K-major, 128-byte swizzle
         const int n = i / (p.K / 4), q = i % (p.K / 4);
         const float4 v = *reinterpret_cast<const float4 *>(p.W + (size_t)n * p.ldw + q * 4);
         *reinterpret_cast<float4 *>(sm.w + (q >> 3) * kChunkBytes + sw128_offset(n, q & 7)) = to_tf32(v);
     }
-    for (int i = tid; i < kBN; i += kTcThreads) {
+    for (int i = tid; i < kBN; i += kTThreads) {
         sm.sbias[i] = p.bias ? p.bias[i] : 0.f;
         if (i < p.K) { sm.sa[i] = p.a ? p.a[i] : 1.f; sm.sb[i] = p.a ? p.b[i] : 0.f; }
     }
@@ -126,168 +120,153 @@ tc_fwd_kernel(const TcFwdParams p)
     tc_fence_after_sync();
     const uint32_t tmem_base = sm.tmem_base;
 
-    if (warp < kFwdMmaWarp) {
-        // ================================ producers ================================
-        // warp w owns channel chunk c = w & 3 (its BatchNorm coefficients live in registers) and row groups 2i + (w >> 2);
-        // one warp instruction = 4 rows x 128 B.  All 16 loads of a tile are in flight before the stage is even free (a rolling
-        // refill pipeline measured 20 % slower: its loads queue behind the transform of the previous tile).
+    if (warp < kTMmaWarp) {
+        // ================================ converters ================================
+        // warp w owns channel chunk c = w & 3 and pixel rows r0 + 8 i (i = 0..7): a warp instruction covers 4 rows x 128 B.
         const int rl = lane >> 3, u = lane & 7;
-        const int pw = warp & 7, grp = warp >> 3;
-        const int c = pw & 3, rg0 = pw >> 2;
+        const int c = warp & 3, r0 = (warp >> 2) * 4 + rl;
         const int k = c * 32 + u * 4;
-        const bool kin = k < p.K;
+        const bool kin = k < p.K, chunk_used = c * 32 < p.K;
         float4 av = make_float4(1.f, 1.f, 1.f, 1.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kin) { av = *reinterpret_cast<const float4 *>(&sm.sa[k]); bv = *reinterpret_cast<const float4 *>(&sm.sb[k]); }
         const bool act = p.a != nullptr && !(GA_ABLATE & 2);
-        {   // work in the log2 domain: z * log2(e) comes straight out of the FMA
+        {   // log2 domain: z * log2(e) comes straight out of the FMA
             const float L2E = 1.44269504089f;
             av.x *= L2E; av.y *= L2E; av.z *= L2E; av.w *= L2E; bv.x *= L2E; bv.y *= L2E; bv.z *= L2E; bv.w *= L2E;
         }
         const int M = p.M, ldx = p.ldx;
-        constexpr int kRowStep = 8;                                  // rows between a thread's consecutive loads
-        const int r0 = rg0 * 4 + rl;                                 // row of group i: r0 + kRowStep i  ->  (r & 7) == (r0 & 7) for every i
+        const uint32_t soff = (uint32_t)c * kTChunk + sw128_offset(r0, u);      // + i * 1024
         const float *x0 = p.X + (size_t)r0 * ldx + k;
-        const size_t tile_stride = (size_t)kBM * ldx;
-        const uint32_t soff = (uint32_t)c * kChunkBytes + sw128_offset(r0, u);      // + i * 8 * 128
-        const bool chunk_used = c * 32 < p.K;
-        auto ldrow = [&](int tile, int i, float4 &v) {
-            const bool ok = kin && (tile * kBM + r0 + kRowStep * i < M);
-            if (GA_ABLATE & 1) { v = make_float4(0.5f, 0.25f, ok ? 0.125f : 0.f, 1.f); return; }
-            v = ok ? *reinterpret_cast<const float4 *>(x0 + (size_t)tile * tile_stride + (size_t)(kRowStep * i) * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        auto issue = [&](int t, int st) {
+            if (!chunk_used || (GA_ABLATE & 1)) return;
+            const uint32_t dst = smem_u32(sm.x[st]) + soff;
+            const float *src = x0 + (size_t)t * kTPx * ldx;
+            const bool whole = (t + 1) * kTPx <= M;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool ok = kin && (whole || t * kTPx + r0 + 8 * i < M);      // rows >= M and channels >= K are zero-filled, never read
+                cp_async16(dst + i * 1024, ok ? src + (size_t)(8 * i) * ldx : p.X, ok);
+            }
         };
-        const int gstep = gridDim.x;
-        for (int it = grp, tile = blockIdx.x + grp * gstep; tile < num_tiles; tile += gstep * kFwdGroups, it += kFwdGroups) {
-            const int s = it & 1, n = it >> 1;
-            float4 v[kFwdRowsPerThread];
-#pragma unroll
-            for (int i = 0; i < kFwdRowsPerThread; ++i) ldrow(tile, i, v[i]);
-            TWAIT(0, warp_wait(&sm.empty[s], (n & 1) ^ 1, lane));
-            unsigned char *dst = sm.a[s] + soff;
+        // the stage of tile t + kTStages is free once the tensor core has read tile t (mma_done): the first refill blocks, the others only probe
+        int tl = blockIdx.x, sl = 0, nl = 0, ahead = 0;
+        auto refill = [&]() {
+            while (ahead < kTLook && tl < num_tiles) {
+                if (ahead == 0) warp_wait(&sm.mma_done[sl], (nl & 1) ^ 1, lane);
+                else if (!warp_test(&sm.mma_done[sl], (nl & 1) ^ 1, lane)) break;
+                issue(tl, sl);
+                cp_async_commit();                         // one group per tile
+                ++ahead; tl += gstep; if (++sl == kTStages) { sl = 0; ++nl; }
+            }
+        };
+        refill();
+        int s = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gstep) {
+            if (ahead >= 3) cp_async_wait<2>(); else if (ahead == 2) cp_async_wait<1>(); else cp_async_wait<0>();
             if (chunk_used) {
+                unsigned char *xs = sm.x[s] + soff;
 #pragma unroll
-                for (int i = 0; i < kFwdRowsPerThread; ++i) {
-                    float4 x = v[i];
+                for (int i = 0; i < 8; ++i) {
+                    float4 x = (GA_ABLATE & 1) ? make_float4(0.5f, 0.25f, 0.125f, 1.f) : *reinterpret_cast<const float4 *>(xs + i * 1024);
                     if (act) {
                         x.x = softplus_log2(fmaf(x.x, av.x, bv.x)); x.y = softplus_log2(fmaf(x.y, av.y, bv.y));
                         x.z = softplus_log2(fmaf(x.z, av.z, bv.z)); x.w = softplus_log2(fmaf(x.w, av.w, bv.w));
                     }
-                    *reinterpret_cast<float4 *>(dst + i * (kRowStep * 128)) = to_tf32(x);
+                    *reinterpret_cast<float4 *>(xs + i * 1024) = to_tf32(x);       // rows >= M hold act(bn(0)): their columns are never stored
                 }
             }
             fence_proxy_async_smem();
             warp_arrive(&sm.full[s], lane);
+            if (++s == kTStages) s = 0;
+            --ahead;
+            refill();
         }
-    } else if (warp == kFwdMmaWarp) {
+    } else if (warp == kTMmaWarp) {
         // ================================ MMA issuer ================================
-        constexpr uint32_t idesc = make_idesc_tf32(kBM, kBN, false, false);
-        const uint32_t w_addr = smem_u32(sm.w);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int s = it & 1, n = it >> 1;
-            TWAIT(0, warp_wait(&sm.full[s], n & 1, lane));
-            TWAIT(1, warp_wait(&sm.tmem_empty[s], (n & 1) ^ 1, lane));
+        constexpr uint32_t idesc = make_idesc_tf32(128, kTPx, false, false);
+        const uint32_t w_lo = desc_lo(smem_u32(sm.w), 16);
+        const int nk = (GA_ABLATE & 4) ? 0 : p.K / 8;               // 16 (K = 128) or 9 (K = 72)
+        int s = 0, n = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gstep) {
+            warp_wait(&sm.full[s], n & 1, lane);
+            warp_wait(&sm.tmem_empty[s], (n & 1) ^ 1, lane);
             tc_fence_after_sync();
             if (lane == 0) {
                 constexpr uint32_t hi = desc_hi(1024);
-                const uint32_t a_lo = desc_lo(smem_u32(sm.a[s]), 16), w_lo = desc_lo(w_addr, 16);
-                const uint32_t d = tmem_base + (uint32_t)s * kBN;
-                const int nk = (GA_ABLATE & 4) ? 0 : p.K / 8;           // 16 (K = 128) or 9 (K = 72)
+                const uint32_t x_lo = desc_lo(smem_u32(sm.x[s]), 16);
+                const uint32_t d = tmem_base + (uint32_t)s * kTPx;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (k < nk) {
-                        constexpr uint32_t kChunk16 = kChunkBytes >> 4;
-                        const uint32_t off = (uint32_t)(k >> 2) * kChunk16 + (uint32_t)(k & 3) * 2u;      // byte offset >> 4
-                        mma_tf32_lohi(d, a_lo + off, w_lo + off, hi, idesc, k > 0);
-                    }
-                }
+                for (int k = 0; k < 16; ++k)
+                    if (k < nk)
+                        mma_tf32_lohi(d, w_lo + (uint32_t)(k >> 2) * (kChunkBytes >> 4) + (uint32_t)(k & 3) * 2u,
+                                      x_lo + (uint32_t)(k >> 2) * (kTChunk >> 4) + (uint32_t)(k & 3) * 2u, hi, idesc, k > 0);
                 mma_commit(&sm.mma_done[s]);
             }
             __syncwarp();
+            if (++s == kTStages) { s = 0; ++n; }
         }
     } else {
-        // ================================ epilogue ================================
-        const int q = warp & 3;                      // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;               // tile row == TMEM lane
-        constexpr int kRowsPerWarp = kBM / kFwdEWarps, kColBlocks = 32 / kFwdEWarps;      // store rows per warp; 16-column blocks staged per warp
-        constexpr int kEpiThreads = kFwdEWarps * 32;
-        const int wr = warp - kFwdEpiWarp0;          // rows [kRowsPerWarp wr, +kRowsPerWarp) of the tile are stored by this warp
-        const int half = wr >> 2;                    // which channel half this warp drains from TMEM (always 0 with 4 warps)
-        const float4 bias4 = *reinterpret_cast<const float4 *>(&sm.sbias[lane * 4]);      // the store phase owns channels 4 lane .. 4 lane + 3
-        double dsum[4] = {0.0, 0.0, 0.0, 0.0}, dsq[4] = {0.0, 0.0, 0.0, 0.0};
+        // ================================ epilogue: one output channel per thread ================================
+        const int ew = warp - kTEpiWarp0, q = warp & 3, half = ew >> 2;
+        const int c = q * 32 + lane;                 // TMEM lane == output channel
+        const float bias = sm.sbias[c];
+        const int ldy = p.ldy;
         const bool accumulate = p.accumulate && !(GA_ABLATE & 16);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int s = it & 1, n = it >> 1;
-            const int m0 = tile * kBM;
-            TWAIT(0, warp_wait(&sm.mma_done[s], n & 1, lane));
-            tc_fence_after_sync();
-            unsigned char *stg = sm.a[s];            // the MMA has finished reading this stage: reuse it as staging
-#pragma unroll 2
-            for (int cb = 0; cb < kColBlocks; ++cb) {
-                const int cc = half * kColBlocks + cb;
-                float v[16];
-                tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * kBN + cc * 16, v);
+        const size_t ystep = (size_t)gstep * kTPx * ldy;
+        float *yp = p.Y + ((size_t)blockIdx.x * kTPx + half * 32) * ldy + c;        // this thread's column, first of its 32 rows
+        double dsum = 0.0, dsq = 0.0;
+        int s = 0, n = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gstep, yp += ystep) {
+            const int rows = p.M - (tile * kTPx + half * 32);                       // valid rows of this warp's slice (may be <= 0 or >= 32)
+            float ev[16];
+            auto ldev = [&](int ph) {                // existing Y (the fan-in's other half): fetched before the accumulator is needed
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<float4 *>(stg + row * 512 + (((cc * 4 + j) ^ (row & 31)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                for (int j = 0; j < 16; ++j) ev[j] = (ph * 16 + j < rows) ? yp[(ph * 16 + j) * ldy] : 0.f;
+            };
+            if (accumulate) ldev(0);
+            warp_wait(&sm.mma_done[s], n & 1, lane);
+            tc_fence_after_sync();
+            float cs = 0.f, cq = 0.f;
+#pragma unroll 1
+            for (int ph = 0; ph < 2; ++ph) {
+                float v[16];
+                tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * kTPx + half * 32 + ph * 16, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += bias;
+                if (accumulate) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += ev[j];
+                    if (ph == 0) ldev(1);
+                }
+                if (rows >= (ph + 1) * 16) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (!(GA_ABLATE & 16)) yp[(ph * 16 + j) * ldy] = v[j];
+                        if (!(GA_ABLATE & 8)) { cs += v[j]; cq = fmaf(v[j], v[j], cq); }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (ph * 16 + j < rows) {
+                            if (!(GA_ABLATE & 16)) yp[(ph * 16 + j) * ldy] = v[j];
+                            if (!(GA_ABLATE & 8)) { cs += v[j]; cq = fmaf(v[j], v[j], cq); }
+                        }
+                }
             }
             tc_fence_before_sync();
             warp_arrive(&sm.tmem_empty[s], lane);          // accumulator drained
-            TWAIT(1, named_bar_sync(1, kEpiThreads));
-            // coalesced row stores (one 512-byte row per warp instruction) + bias + the BatchNorm statistics of this warp's rows
-            const int rows = p.M - m0 - wr * kRowsPerWarp;  // valid rows of this warp's slice (may be <= 0 or > kRowsPerWarp)
-            float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = cs;
-            const unsigned char *sp0 = stg + (wr * kRowsPerWarp) * 512;
-            float *gp0 = p.Y + (size_t)(m0 + wr * kRowsPerWarp) * p.ldy + lane * 4;
-#pragma unroll 1
-            for (int i0 = 0; i0 < kRowsPerWarp; i0 += 4) {
-                float4 e[4];
-                if (accumulate) {              // the existing rows are fetched four at a time so that one memory latency covers them all
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        e[k] = (i0 + k < rows) ? *reinterpret_cast<const float4 *>(gp0 + (size_t)(i0 + k) * p.ldy) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int i = i0 + k;
-                    if (i < rows) {
-                        float4 o = *reinterpret_cast<const float4 *>(sp0 + i * 512 + ((lane ^ ((wr * kRowsPerWarp + i) & 31)) << 4));
-                        o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
-                        if (accumulate) { o.x += e[k].x; o.y += e[k].y; o.z += e[k].z; o.w += e[k].w; }
-                        if (!(GA_ABLATE & 16)) *reinterpret_cast<float4 *>(gp0 + (size_t)i * p.ldy) = o;
-                        if (!(GA_ABLATE & 8)) {
-                            cs.x += o.x; cs.y += o.y; cs.z += o.z; cs.w += o.w;
-                            cq.x = fmaf(o.x, o.x, cq.x); cq.y = fmaf(o.y, o.y, cq.y); cq.z = fmaf(o.z, o.z, cq.z); cq.w = fmaf(o.w, o.w, cq.w);
-                        }
-                    }
-                }
-            }
-            dsum[0] += (double)cs.x; dsum[1] += (double)cs.y; dsum[2] += (double)cs.z; dsum[3] += (double)cs.w;
-            dsq[0] += (double)cq.x; dsq[1] += (double)cq.y; dsq[2] += (double)cq.z; dsq[3] += (double)cq.w;
-            warp_arrive(&sm.empty[s], lane);               // staging consumed: the producers may refill this stage
+            dsum += (double)cs; dsq += (double)cq;
+            if (++s == kTStages) { s = 0; ++n; }
         }
-        if (p.sum) {
-            // combine the warps' partial sums through shared memory (stage 0 is idle by now): 2 atomics per channel per CTA
-            double *red = reinterpret_cast<double *>(sm.a[0]);
-            named_bar_sync(1, kEpiThreads);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { red[(wr * 8 + k) * 32 + lane] = dsum[k]; red[(wr * 8 + 4 + k) * 32 + lane] = dsq[k]; }
-            named_bar_sync(1, kEpiThreads);
-            if (wr < 4) {
-                const int et = wr * 32 + lane, l = et >> 2, k = et & 3;      // channel et = 4 l + k
-                double ts = 0.0, tq = 0.0;
-#pragma unroll
-                for (int w = 0; w < kFwdEWarps; ++w) { ts += red[(w * 8 + k) * 32 + l]; tq += red[(w * 8 + 4 + k) * 32 + l]; }
-                atomicAdd(&p.sum[et], ts); atomicAdd(&p.sumsq[et], tq);
-            }
+        if (p.sum) {                                 // the two pixel halves of a channel meet in shared memory: 2 atomics per channel per CTA
+            if (half == 1) { sm.red[0][c] = dsum; sm.red[1][c] = dsq; }
+            named_bar_sync(1, 8 * 32);
+            if (half == 0) { atomicAdd(&p.sum[c], dsum + sm.red[0][c]); atomicAdd(&p.sumsq[c], dsq + sm.red[1][c]); }
         }
     }
-#if GA_TC_TIMING
-    if (blockIdx.x == 0 && lane == 0) printf("TCT fwd K=%d warp %d total %lld wait0 %lld wait1 %lld tiles %d\n", p.K, warp, clock64() - tstart_, tw_[0], tw_[1], (num_tiles + (int)gridDim.x - 1) / (int)gridDim.x);
-#endif
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == kFwdMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == kTMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 }  // namespace
@@ -298,17 +277,17 @@ int launch_tc_fwd(const float *X, int ldx, int K, const float *a, const float *b
 {
     GA_REQUIRE(K % 8 == 0 && K >= 8 && K <= 128, "tcgen05 layer: K=%d must be a multiple of 8 in [8,128]", K);
     GA_REQUIRE(ldx % 4 == 0 && ldw % 4 == 0 && ldy % 4 == 0, "tcgen05 layer: leading dimensions must be multiples of 4");
-    static bool attr_set = false;
-    if (!attr_set) {
-        GA_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcFwdSmem) + 1024));
-        attr_set = true;
-    }
     TcFwdParams p{X, ldx, K, a, b, W, ldw, bias, Y, ldy, accumulate, sum, sumsq, M};
-    const int tiles = cdiv(M, kBM);
+    static bool attr_t_set = false;
+    if (!attr_t_set) {
+        GA_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcFwdTSmem) + 1024));
+        attr_t_set = true;
+    }
+    const int tiles = cdiv(M, kTPx);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
     {
         ProfScope _ps("mlp_tc_fwd", st);
-        launch_k(tc_fwd_kernel, grid, kTcThreads, sizeof(TcFwdSmem) + 1024, st, p);
+        launch_k(tc_fwd_kernel, grid, kTThreads, sizeof(TcFwdTSmem) + 1024, st, p);
     }
     GA_CHECK_LAUNCH("tc_fwd_kernel");
     return GA_OK;
@@ -359,6 +338,9 @@ constexpr int kGkTile = 4 * kGkChunk;     // 16 KB
 constexpr int kMnTile = 4 * kGkChunk;     // 16 KB: MN-major image [4 x 32-channel chunks][32 px][128 B] (32-byte-base swizzle)
 #ifndef GA_BWD_EWARPS
 #define GA_BWD_EWARPS 8
+#endif
+#ifndef GA_BWD_G_MMADONE
+#define GA_BWD_G_MMADONE 1
 #endif
 #ifndef GA_BWD_LOOK
 #define GA_BWD_LOOK 2
@@ -502,8 +484,9 @@ tc_bwd_kernel(const TcBwdParams p)
             int tl = tile, sl = 0, nl = 0, ahead = 0;      // next tile to copy, its stage / round; tiles copied but not yet converted
             auto refill = [&]() {
                 while (ahead < kLook && tl < num_tiles) {
-                    if (ahead == 0) TWAIT(0, warp_wait(&sm.empty[sl], (nl & 1) ^ 1, lane));
-                    else if (!warp_test(&sm.empty[sl], (nl & 1) ^ 1, lane)) break;
+                    uint64_t *freed = GA_BWD_G_MMADONE ? &sm.mma_done[sl] : &sm.empty[sl];   // the epilogue never touches the G images
+                    if (ahead == 0) TWAIT(0, warp_wait(freed, (nl & 1) ^ 1, lane));
+                    else if (!warp_test(freed, (nl & 1) ^ 1, lane)) break;
                     issue(tl, sl);
                     cp_async_commit();                     // one group per tile
                     ++ahead; tl += gstep; if (++sl == kBStages) { sl = 0; ++nl; }
@@ -539,6 +522,7 @@ tc_bwd_kernel(const TcBwdParams p)
         } else {
             const int ldp = p.ldp;
             const bool raw = p.x_raw != 0 || (GA_ABLATE & 2);
+            const bool x_read_by_epilogue = (p.mode == 0 || p.mode == 3) && !(GA_ABLATE & 8);      // final modes recover sigmoid / xhat from the X tile
             const float4 av = *reinterpret_cast<const float4 *>(&sm.pa[ch]), bv = *reinterpret_cast<const float4 *>(&sm.pb[ch]);
             const bool okc = ch < p.kin;
             const float *x0 = p.Yprev + (size_t)p0 * ldp + ch;
@@ -559,8 +543,9 @@ tc_bwd_kernel(const TcBwdParams p)
             int tl = tile, sl = 0, nl = 0, ahead = 0;
             auto refill = [&]() {
                 while (ahead < kLook && tl < num_tiles) {
-                    if (ahead == 0) TWAIT(0, warp_wait(&sm.empty[sl], (nl & 1) ^ 1, lane));
-                    else if (!warp_test(&sm.empty[sl], (nl & 1) ^ 1, lane)) break;
+                    uint64_t *freed = (GA_BWD_G_MMADONE && !x_read_by_epilogue) ? &sm.mma_done[sl] : &sm.empty[sl];
+                    if (ahead == 0) TWAIT(0, warp_wait(freed, (nl & 1) ^ 1, lane));
+                    else if (!warp_test(freed, (nl & 1) ^ 1, lane)) break;
                     issue(tl, sl);
                     cp_async_commit();
                     ++ahead; tl += gstep; if (++sl == kBStages) { sl = 0; ++nl; }
