@@ -331,8 +331,15 @@ extern "C" int ga_tc_linear_forward(int32_t M, int32_t K, const float *X, int32_
 namespace ga {
 namespace {
 
-constexpr int kPx = 32;
-constexpr int kBStages = 3;
+#ifndef GA_BWD_PX
+#define GA_BWD_PX 32
+#endif
+constexpr int kPx = GA_BWD_PX;            // pixels per tile: 32, or 64 (two stages) when W^T lives in tensor memory
+constexpr int kBlk = kPx / 8, kPh = kPx / 16;
+#ifndef GA_BWD_WT_TMEM
+#define GA_BWD_WT_TMEM 1
+#endif
+constexpr int kBStages = GA_BWD_PX == 64 ? 2 : GA_BWD_PX == 48 ? 3 : GA_BWD_WT_TMEM ? 4 : 3;   // W^T in tensor memory frees 64 KB of shared memory: a fourth 48 KB stage
 constexpr int kGkChunk = kPx * 128;       // 4 KB: [32 px rows][32 channels]
 constexpr int kGkTile = 4 * kGkChunk;     // 16 KB
 constexpr int kMnTile = 4 * kGkChunk;     // 16 KB: MN-major image [4 x 32-channel chunks][32 px][128 B] (32-byte-base swizzle)
@@ -343,13 +350,14 @@ constexpr int kMnTile = 4 * kGkChunk;     // 16 KB: MN-major image [4 x 32-chann
 #define GA_BWD_G_MMADONE 1
 #endif
 #ifndef GA_BWD_LOOK
-#define GA_BWD_LOOK 2
+#define GA_BWD_LOOK (GA_BWD_PX == 64 ? 1 : GA_BWD_PX == 48 ? 2 : GA_BWD_WT_TMEM ? 3 : 2)
 #endif
 constexpr int kLook = GA_BWD_LOOK;               // tiles of raw operand copies in flight per producer thread (1 or 2; < kBStages)
 constexpr int kBwdEWarps = GA_BWD_EWARPS;  // epilogue warps: 4 (each 2 x 16 pixels) or 8 (two per TMEM lane quarter, 16 pixels each)
 constexpr int kBwdThreads = (17 + kBwdEWarps) * 32;      // 8 G-producer warps, 8 X-producer warps, 1 MMA warp, epilogue warps
 constexpr int kBwdMmaWarp = 16, kBwdEpiWarp0 = 17;
-constexpr uint32_t kBwdTmemCols = 256;    // [0,128): dW accumulator; 128 + 32 s: dX^T accumulator of stage s
+constexpr uint32_t kBwdTmemCols = GA_BWD_WT_TMEM ? 512 : 256;    // [0,128): dW accumulator; 128 + 32 s: dX^T accumulator of stage s; [256,384): W^T
+constexpr uint32_t kWtCol = 256;
 
 struct TcBwdParams {
     const float *dZ, *Y; int ldg;                      // layer l: [M][ldg], 128 output channels from the pointer
@@ -367,7 +375,9 @@ struct TcBwdParams {
 };
 
 struct alignas(1024) TcBwdSmem {
+#if !GA_BWD_WT_TMEM
     unsigned char wt[4 * 128 * 128];                   // 64 KB: W^T, rows = input channel, K = output channel
+#endif
     unsigned char gk[kBStages][kGkTile];               // G   rows = pixel,          K = output channel   (dgrad B operand)
     unsigned char gm[kBStages][kMnTile];               // G   MN-major: M = output channel, K = pixel     (wgrad A operand)
     unsigned char xm[kBStages][kMnTile];               // X   MN-major: N = input channel,  K = pixel     (wgrad B operand)
@@ -398,6 +408,7 @@ tc_bwd_kernel(const TcBwdParams p)
     }
     if (warp == kBwdMmaWarp) tmem_alloc(&sm.tmem_base, kBwdTmemCols);
     pdl_wait();            // barrier init and TMEM allocation above overlap the previous kernel's tail
+#if !GA_BWD_WT_TMEM
     // W^T -> shared (K-major over the OUTPUT channel): element (in, out) <- W[out][in]
     // thread = (input channel, group of 4 output channels): four coalesced row reads of W, ONE 16-byte store of the transposed quad
     // (the 8 lanes of a store phase have 8 different `in & 7`, hence 8 different 16-byte units: conflict-free)
@@ -409,6 +420,7 @@ tc_bwd_kernel(const TcBwdParams p)
             *reinterpret_cast<float4 *>(sm.wt + (o >> 5) * (128 * 128) + in * 128 + ((((o & 31) >> 2) ^ (in & 7)) << 4)) = v;
         }
     }
+#endif
     for (int i = tid; i < 128; i += kBwdThreads) {
         if (p.ga) {   // ga (dZ - m1 - (Y - mu) rstd m2)
             const float ga = p.ga[i], k = p.rstd[i] * p.m2[i];
@@ -428,6 +440,25 @@ tc_bwd_kernel(const TcBwdParams p)
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = sm.tmem_base;
+#if GA_BWD_WT_TMEM
+    // W^T -> TENSOR MEMORY: the dgrad's A operand (rows = input channel = TMEM lane, one column per output channel) is read by the
+    // tensor core from there, so it costs neither shared memory (64 KB) nor shared-memory bandwidth (it was re-read for every tile).
+    // Four warps, one per lane quarter: lanes read W[out][in] coalesced over `in`.
+    if (warp >= kBwdEpiWarp0 && warp < kBwdEpiWarp0 + 4) {
+        const int in = (warp & 3) * 32 + lane;
+        const float *wp = p.W + in;
+#pragma unroll 1
+        for (int cc = 0; cc < 8; ++cc) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = in < p.kin ? to_tf32(wp[(size_t)(cc * 16 + j) * p.ldw]) : 0.f;
+            tmem_st_32x16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kWtCol + cc * 16, v);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+#endif
 #if GA_TC_TIMING
     const long long tpro_ = clock64() - tstart_;
     long long tloop_ = 0;
@@ -466,18 +497,31 @@ tc_bwd_kernel(const TcBwdParams p)
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const int row8 = 8 * ldg;
             const ptrdiff_t ydelta = y0 - dz0;
+            // running source pointer of the NEXT tile to copy, stage addresses as base + stage * size: a whole tile (every tile but possibly
+            // the last) is 8 plain copies with no predicate or select -- this bookkeeping used to be 15 % of the kernel's instructions
+            const float *pz = dz0 + (size_t)tile * tile_stride;
+            const size_t pstep = (size_t)gstep * tile_stride;
+            const uint32_t dk0 = smem_u32(sm.gk[0]) + k_off, dm0 = smem_u32(sm.gm[0]) + mn_off;
             auto issue = [&](int t, int st) {
-                if (GA_ABLATE & 1) return;
-                const uint32_t dk = smem_u32(sm.gk[st]) + k_off, dm = smem_u32(sm.gm[st]) + mn_off;
-                const float *pz = dz0 + (size_t)t * tile_stride;
-                const bool whole = (t + 1) * kPx <= M;
+                if (!(GA_ABLATE & 1)) {
+                    const uint32_t dk = dk0 + (uint32_t)st * kGkTile, dm = dm0 + (uint32_t)st * kMnTile;
+                    if ((t + 1) * kPx <= M) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const bool ok = whole || t * kPx + e * 8 + p0 < M;
-                    const float *src = ok ? pz + e * row8 : dz0;
-                    cp_async16(dk + e * 1024, src, ok);
-                    if (has_y) cp_async16(dm + e * 1024, ok ? src + ydelta : dz0, ok);
+                        for (int e = 0; e < kBlk; ++e) cp_async16_full(dk + e * 1024, pz + e * row8);
+                        if (has_y) {
+#pragma unroll
+                            for (int e = 0; e < kBlk; ++e) cp_async16_full(dm + e * 1024, pz + ydelta + e * row8);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < kBlk; ++e) {
+                            const bool ok = t * kPx + e * 8 + p0 < M;          // rows >= M are zero-filled
+                            cp_async16(dk + e * 1024, ok ? pz + e * row8 : dz0, ok);
+                            if (has_y) cp_async16(dm + e * 1024, ok ? pz + ydelta + e * row8 : dz0, ok);
+                        }
+                    }
                 }
+                pz += pstep;
             };
             // Copies run up to two tiles ahead.  The stage of the tile after next is the one the epilogue frees LAST, so it is only probed:
             // if it is still busy the copy is issued one iteration later (blocking then would serialise conversion behind the epilogue).
@@ -494,11 +538,11 @@ tc_bwd_kernel(const TcBwdParams p)
             };
             refill();
             for (; tile < num_tiles; tile += gstep) {
-                if (ahead >= 2) cp_async_wait<1>(); else cp_async_wait<0>();      // this tile's pieces have landed (a younger group stays in flight)
+                if (ahead >= 3) cp_async_wait<2>(); else if (ahead == 2) cp_async_wait<1>(); else cp_async_wait<0>();      // this tile's pieces have landed (younger groups stay in flight)
                 unsigned char *gk = sm.gk[s] + k_off, *gm = sm.gm[s] + mn_off;
                 const bool ragged = (tile + 1) * kPx > M;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < kBlk; ++e) {
                     float4 za, ya;
                     if (GA_ABLATE & 1) { za = ya = make_float4(0.5f, 0.25f, 0.125f, 1.f); }
                     else {
@@ -529,16 +573,24 @@ tc_bwd_kernel(const TcBwdParams p)
             const size_t tile_stride = (size_t)kPx * ldp;
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
             const int row8 = 8 * ldp;
+            const float *px = x0 + (size_t)tile * tile_stride;
+            const size_t pstep = (size_t)gstep * tile_stride;
+            const uint32_t dm0 = smem_u32(sm.xm[0]) + mn_off;
             auto issue = [&](int t, int st) {
-                if (GA_ABLATE & 1) return;
-                const uint32_t dm = smem_u32(sm.xm[st]) + mn_off;
-                const float *px = x0 + (size_t)t * tile_stride;
-                const bool whole = (t + 1) * kPx <= M;
+                if (!(GA_ABLATE & 1)) {
+                    const uint32_t dm = dm0 + (uint32_t)st * kMnTile;
+                    if (okc && (t + 1) * kPx <= M) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const bool ok = okc && (whole || t * kPx + e * 8 + p0 < M);     // channels past kin (the 72-wide input layer) are never read
-                    cp_async16(dm + e * 1024, ok ? px + e * row8 : p.Yprev, ok);
+                        for (int e = 0; e < kBlk; ++e) cp_async16_full(dm + e * 1024, px + e * row8);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < kBlk; ++e) {
+                            const bool ok = okc && t * kPx + e * 8 + p0 < M;     // channels past kin (the 72-wide input layer) are never read
+                            cp_async16(dm + e * 1024, ok ? px + e * row8 : p.Yprev, ok);
+                        }
+                    }
                 }
+                px += pstep;
             };
             int tl = tile, sl = 0, nl = 0, ahead = 0;
             auto refill = [&]() {
@@ -553,11 +605,11 @@ tc_bwd_kernel(const TcBwdParams p)
             };
             refill();
             for (; tile < num_tiles; tile += gstep) {
-                if (ahead >= 2) cp_async_wait<1>(); else cp_async_wait<0>();
+                if (ahead >= 3) cp_async_wait<2>(); else if (ahead == 2) cp_async_wait<1>(); else cp_async_wait<0>();
                 unsigned char *xm = sm.xm[s] + mn_off;
                 const bool ragged = (tile + 1) * kPx > M;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
+                for (int e = 0; e < kBlk; ++e) {
                     float4 o = (GA_ABLATE & 1) ? make_float4(0.5f, 0.25f, 0.125f, 1.f) : *reinterpret_cast<const float4 *>(xm + e * 1024);
                     if (!raw) {
                         o.x = softplus_log2(fmaf(o.x, av.x, bv.x)); o.y = softplus_log2(fmaf(o.y, av.y, bv.y));
@@ -577,7 +629,9 @@ tc_bwd_kernel(const TcBwdParams p)
         // ================================ MMA issuer ================================
         constexpr uint32_t idesc_dgrad = make_idesc_tf32(128, kPx, false, false);
         constexpr uint32_t idesc_wgrad = make_idesc_tf32(128, 128, true, true);      // both operands MN-major (K = pixel)
+#if !GA_BWD_WT_TMEM
         const uint32_t wt_addr = smem_u32(sm.wt);
+#endif
         int it = 0, s = 0, n = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             TWAIT(0, warp_wait(&sm.full[s], n & 1, lane));
@@ -589,14 +643,21 @@ tc_bwd_kernel(const TcBwdParams p)
                 constexpr uint32_t hi = desc_hi(1024);
                 // MN-major images: 32-channel chunks kGkChunk apart (LBO), 4-pixel swizzle atoms 512 B apart (SBO), layout type 1
                 constexpr uint32_t hi_mn = (512u >> 4) | (1u << 14) | (1u << 29);
-                const uint32_t wt_lo = desc_lo(wt_addr, 16), gk_lo = desc_lo(smem_u32(sm.gk[s]), 16), gm_lo = desc_lo(smem_u32(sm.gm[s]), kGkChunk),
+#if !GA_BWD_WT_TMEM
+                const uint32_t wt_lo = desc_lo(wt_addr, 16);
+#endif
+                const uint32_t gk_lo = desc_lo(smem_u32(sm.gk[s]), 16), gm_lo = desc_lo(smem_u32(sm.gm[s]), kGkChunk),
                                xm_lo = desc_lo(smem_u32(sm.xm[s]), kGkChunk);
                 const uint32_t d_dx = tmem_base + 128 + (uint32_t)s * kPx;
                 // dX^T[in, px] = sum_out W^T[in, out] G[px, out]: 16 steps of 8 output channels
 #pragma unroll
                 for (int k = 0; k < 16; ++k)
+#if GA_BWD_WT_TMEM
+                    mma_tf32_ts(d_dx, tmem_base + kWtCol + (uint32_t)k * 8u, gk_lo + (uint32_t)(k >> 2) * (kGkChunk >> 4) + (uint32_t)(k & 3) * 2u, hi, idesc_dgrad, k > 0);
+#else
                     mma_tf32_lohi(d_dx, wt_lo + (uint32_t)(k >> 2) * ((128 * 128) >> 4) + (uint32_t)(k & 3) * 2u,
                                   gk_lo + (uint32_t)(k >> 2) * (kGkChunk >> 4) + (uint32_t)(k & 3) * 2u, hi, idesc_dgrad, k > 0);
+#endif
                 // dW[out, in] += sum_px G^T[out, px] X^T[in, px]: 4 steps of 8 pixels
 #pragma unroll
                 for (int j = 0; j < kPx / 8; ++j)
@@ -652,13 +713,13 @@ tc_bwd_kernel(const TcBwdParams p)
             TMARK(te_);
             float t1 = 0.f, t2 = 0.f;
 #pragma unroll 1
-            for (int ph = ew >> 2; ph < 2; ph += kPhStep) {
+            for (int ph = ew >> 2; ph < kPh; ph += kPhStep) {
                 float v[16];
                 tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + 128 + (uint32_t)s * kPx + ph * 16, v);
                 if (add_existing) {
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += ev[j];
-                    if (ph + kPhStep < 2) ldev(ph + kPhStep);
+                    if (ph + kPhStep < kPh) ldev(ph + kPhStep);
                 }
                 if (final_mode) {
                     const unsigned char *xr = sm.xm[s] + ph * (16 * 128);

@@ -44,10 +44,12 @@ geo = (torch.randn(1, 64, 128, 128) * 0.01).cuda().requires_grad_(True)
 def step():
     dec = net.forward_packed(geo, {S}, 2); dec.backward(torch.ones_like(dec) * 1e-3)
 for _ in range(2): step()
+net.zero_grad(); geo.grad = None; step()
+chk = "chk dgeo=%.6e dflat=%.6e" % (geo.grad.double().abs().sum().item(), sum(p.grad.double().abs().sum().item() for p in net.parameters() if p.grad is not None))
 torch.cuda.synchronize(); L.profile(True)
 for _ in range({iters}): step()
 rep = L.profile_report()
-print({os.path.basename(path)!r}, " ".join(f"{{k}}={{v[1]/{iters}:.3f}}ms/{{v[0]//{iters}}}" for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1]) if k.startswith(("mlp_tc", "heads", "geom_conv", "sample_feat"))))
+print({os.path.basename(path)!r}, chk, " ".join(f"{{k}}={{v[1]/{iters}:.3f}}ms/{{v[0]//{iters}}}" for k, v in sorted(rep.items(), key=lambda kv: -kv[1][1]) if k.startswith(("mlp_tc", "heads", "geom_conv", "sample_feat"))))
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     print(r.stdout.strip() or ("FAILED " + os.path.basename(path) + "\n" + r.stderr[-800:]))
