@@ -336,10 +336,11 @@ namespace {
 #endif
 constexpr int kPx = GA_BWD_PX;            // pixels per tile: 32, or 64 (two stages) when W^T lives in tensor memory
 constexpr int kBlk = kPx / 8, kPh = kPx / 16;
+static_assert(kPx == 32 || kPx == 64, "tc_bwd tile: 32 pixels (default) or 64; 48 was measured (no gain) and is not supported");
 #ifndef GA_BWD_WT_TMEM
 #define GA_BWD_WT_TMEM 1
 #endif
-constexpr int kBStages = GA_BWD_PX == 64 ? 2 : GA_BWD_PX == 48 ? 3 : GA_BWD_WT_TMEM ? 4 : 3;   // W^T in tensor memory frees 64 KB of shared memory: a fourth 48 KB stage
+constexpr int kBStages = GA_BWD_PX == 64 ? 2 : GA_BWD_WT_TMEM ? 4 : 3;   // W^T in tensor memory frees 64 KB of shared memory: a fourth 48 KB stage
 constexpr int kGkChunk = kPx * 128;       // 4 KB: [32 px rows][32 channels]
 constexpr int kGkTile = 4 * kGkChunk;     // 16 KB
 constexpr int kMnTile = 4 * kGkChunk;     // 16 KB: MN-major image [4 x 32-channel chunks][32 px][128 B] (32-byte-base swizzle)
@@ -350,7 +351,7 @@ constexpr int kMnTile = 4 * kGkChunk;     // 16 KB: MN-major image [4 x 32-chann
 #define GA_BWD_G_MMADONE 1
 #endif
 #ifndef GA_BWD_LOOK
-#define GA_BWD_LOOK (GA_BWD_PX == 64 ? 1 : GA_BWD_PX == 48 ? 2 : GA_BWD_WT_TMEM ? 3 : 2)
+#define GA_BWD_LOOK (GA_BWD_PX == 64 ? 1 : GA_BWD_WT_TMEM ? 3 : 2)
 #endif
 constexpr int kLook = GA_BWD_LOOK;               // tiles of raw operand copies in flight per producer thread (1 or 2; < kBStages)
 constexpr int kBwdEWarps = GA_BWD_EWARPS;  // epilogue warps: 4 (each 2 x 16 pixels) or 8 (two per TMEM lane quarter, 16 pixels each)
