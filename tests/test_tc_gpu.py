@@ -30,7 +30,9 @@ def tf32_trunc(t):
 
 
 @pytest.mark.parametrize("M,K,act,acc", [(128, 128, False, False), (1024, 128, True, False), (5000, 72, False, False),
-                                         (128 * 300, 128, True, True), (2304, 128, True, False)])
+                                         (128 * 300, 128, True, True), (2304, 128, True, False),
+                                         (1000, 128, True, True),      # ragged last 64-pixel tile (40 rows: the second pixel half has 8) + fan-in accumulate
+                                         (40, 72, True, True), (64 * 148 * 5 + 33, 128, False, False)])      # less than one tile; > 4 stage rounds per CTA
 def test_tc_linear_forward(M, K, act, acc):
     g = torch.Generator().manual_seed(M + K)
     X = torch.randn(M, K, generator=g).to(DEV)
