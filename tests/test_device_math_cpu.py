@@ -133,3 +133,87 @@ def test_umma_layout_helpers_match_the_decoded_hardware_layout(tmp_path):
     r = subprocess.run([cxx, "-std=c++17", "-O1", "-o", str(exe), str(cpp)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout.strip() == "0"
+
+
+def _c_expr(src: str, pattern: str) -> str:
+    """One C initialiser lifted from the product source, turned into a Python expression (casts and integer suffixes dropped)."""
+    m = re.search(pattern, src)
+    assert m, pattern
+    e = m.group(1)
+    e = re.sub(r"\(uint32_t\)", "", e)
+    e = re.sub(r"(\d+)u\b", r"\1", e)
+    return e
+
+
+def test_tc_bwd_piece_addresses_are_the_umma_images():
+    """mlp_tc.cu, backward layer: the cp.async destinations / in-place conversion addresses of the 16 converter warps (`k_off`, `mn_off`)
+    and the epilogue's read-back of x (`xoff`), lifted from the kernel source as written, against the two operand layouts the tensor
+    core consumes: K-major with the 128-byte swizzle (16-byte units XOR px % 8) and MN-major with the 32-byte-base swizzle decoded on the
+    device (tools/exp_umma_probe.cu; formula in the kernel's comment).  Every thread must own whole 16-byte pieces, the pieces of one
+    array must tile the 32-pixel x 128-channel image exactly once, and the epilogue thread of channel c must read element (px, c)."""
+    src = open(os.path.join(ROOT, "gaussianavatar_b200", "csrc", "mlp_tc.cu")).read()
+    k_off = _c_expr(src, r"const uint32_t k_off = (.*?);\s")
+    mn_off = _c_expr(src, r"const uint32_t mn_off = (.*?);\n")
+    xoff = _c_expr(src, r"xoff\[i\] = (.*?);\n")
+    kPx = 32
+    kGkChunk = kPx * 128
+
+    def byte_k(px, ch):      # K-major, SWIZZLE_128B: rows = pixel, 32-channel chunks kGkChunk apart
+        return (ch // 32) * kGkChunk + px * 128 + ((((ch % 32) // 4) ^ (px % 8)) * 16) + (ch % 4) * 4
+
+    def byte_mn(px, c):      # MN-major, SWIZZLE_128B with a 32-byte base (UMMA layout type 1): LBO = chunk, SBO = 512 B per 4 pixels
+        return (c // 32) * kGkChunk + (px // 4) * 512 + (px % 4) * 128 + ((((c % 32) // 8) ^ (px % 4)) * 32) + (c % 8) * 4
+
+    seen_k, seen_mn = set(), set()
+    for warp in range(8):                       # G converters; the X converters (warps 8-15) use pw = warp & 7 -> the same mapping
+        for lane in range(32):
+            c16, pxl = lane & 7, lane >> 3
+            pw = warp & 7
+            j, p0 = pw & 3, (pw >> 2) * 4 + pxl
+            ch = j * 32 + c16 * 4
+            env = dict(j=j, p0=p0, c16=c16, pxl=pxl, kGkChunk=kGkChunk)
+            ko, mo = eval(k_off, {}, env), eval(mn_off, {}, env)
+            for e in range(kPx // 8):
+                px = p0 + 8 * e
+                for i in range(4):              # the four channels of the 16-byte piece are contiguous in both images
+                    assert ko + e * 1024 + 4 * i == byte_k(px, ch + i), (warp, lane, e, i)
+                    assert mo + e * 1024 + 4 * i == byte_mn(px, ch + i), (warp, lane, e, i)
+                seen_k.add(ko + e * 1024); seen_mn.add(mo + e * 1024)
+    assert seen_k == set(range(0, 4 * kGkChunk, 16)) and seen_mn == set(range(0, 4 * kGkChunk, 16))      # each image tiled exactly once
+
+    for q in range(4):                          # epilogue: thread = input channel c, reads x(px, c) from the MN-major X image
+        for lane in range(32):
+            c = q * 32 + lane
+            for i in range(4):
+                xo = eval(xoff, {}, dict(c=c, lane=lane, i=i, kGkChunk=kGkChunk))
+                for ph in range(kPx // 16):
+                    for jj in range(i, 16, 4):  # the kernel indexes xoff[j & 3]
+                        px = ph * 16 + jj
+                        assert ph * 16 * 128 + jj * 128 + xo == byte_mn(px, c), (q, lane, ph, jj)
+
+
+def test_tc_fwd_piece_addresses_are_the_umma_image():
+    """mlp_tc.cu, forward layer: converter thread (warp w, lane) owns chunk c = w & 3, rows r0 + 8 i; its piece address
+    `c * kTChunk + sw128_offset(r0, u) + i * 1024` (lifted) must be the K-major 128-byte-swizzle address of (row, channel) in a 64-row
+    tile, and the 256 threads x 8 pieces must tile the 32 KB stage exactly once."""
+    src = open(os.path.join(ROOT, "gaussianavatar_b200", "csrc", "mlp_tc.cu")).read()
+    tcc = open(os.path.join(ROOT, "gaussianavatar_b200", "csrc", "tc_common.cuh")).read()
+    soff = _c_expr(src, r"const uint32_t soff = (.*?);\s")
+    sw = re.search(r"uint32_t sw128_offset\(int r, int u\) \{ return (.*?); \}", tcc)
+    assert sw
+    sw_expr = re.sub(r"(\d+)u\b", r"\1", re.sub(r"\(uint32_t\)", "", sw.group(1)))
+    sw128_offset = lambda r, u: eval(sw_expr, {}, dict(r=r, u=u))
+    kTPx = 64
+    kTChunk = kTPx * 128
+    seen = set()
+    for warp in range(8):
+        for lane in range(32):
+            rl, u = lane >> 3, lane & 7
+            c, r0 = warp & 3, (warp >> 2) * 4 + rl
+            base = eval(soff, {"sw128_offset": sw128_offset}, dict(c=c, r0=r0, u=u, kTChunk=kTChunk))
+            for i in range(8):
+                row, ch = r0 + 8 * i, c * 32 + u * 4
+                want = (ch // 32) * kTChunk + row * 128 + ((((ch % 32) // 4) ^ (row % 8)) * 16)
+                assert base + i * 1024 == want, (warp, lane, i)
+                seen.add(base + i * 1024)
+    assert seen == set(range(0, 4 * kTChunk, 16))
