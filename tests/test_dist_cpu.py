@@ -101,3 +101,58 @@ def test_pose_embedding_gradients_are_synchronised_across_ranks_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=10) is True
+
+
+def _syncbn_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from gaussianavatar_b200.pose_encoder import UnetNoCond5DS
+    g = torch.Generator().manual_seed(7)
+    x_all = torch.randn(world, 3, 32, 32, generator=g)             # one frame per rank
+    w_all = torch.randn(world, 5, 32, 32, generator=g)             # a different loss weight per frame
+    torch.manual_seed(11)
+    ref = UnetNoCond5DS(input_nc=3, output_nc=5, nf=8).double()
+    sd = {k: v.clone() for k, v in ref.state_dict().items()}
+    # single process, whole batch: the statistics every BatchNorm should see
+    (ref(x_all.double()) * w_all.double()).sum().backward()
+    # this rank: its own frame only, BatchNorm sums all-reduced over the group
+    net = UnetNoCond5DS(input_nc=3, output_nc=5, nf=8).double()
+    net.load_state_dict(sd)
+    net.sync_group = True
+    y = net(x_all[rank:rank + 1].double())
+    (y * w_all[rank:rank + 1].double()).sum().backward()
+    ok = True
+    with torch.no_grad():
+        y_ref = ref(x_all.double())[rank:rank + 1]                 # (second forward of `ref`: only its running statistics move again)
+    ok &= torch.allclose(y, y_ref, rtol=1e-9, atol=1e-10)
+    for (n, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+        gsum = p.grad.clone()
+        dist.all_reduce(gsum)                                      # what the trainer's gradient bucket does for the shared parameters
+        ok &= torch.allclose(gsum, q.grad, rtol=1e-7, atol=1e-9)
+    # running statistics: momentum update with the GLOBAL batch mean / unbiased variance on every rank
+    ref1 = UnetNoCond5DS(input_nc=3, output_nc=5, nf=8).double()
+    ref1.load_state_dict(sd)
+    ref1(x_all.double())
+    for (n, b), (_, c) in zip(net.named_buffers(), ref1.named_buffers()):
+        ok &= torch.allclose(b.double(), c.double(), rtol=1e-9, atol=1e-12)
+    if rank == 0:
+        out.put(bool(ok))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pose_encoder_batchnorm_uses_global_batch_statistics_gloo():
+    """SURVEY.md §8e, stage 2 under data parallelism: with `sync_group` set, every BatchNorm of the pose encoder normalises with the
+    statistics of the GLOBAL batch — 2 ranks x 1 frame give the outputs, the (summed) parameter gradients and the running statistics of
+    1 process x 2 frames, exactly (fp64)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_syncbn_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10) is True
