@@ -67,6 +67,20 @@ struct Carver {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute (opt-in to > 48 KB of dynamic shared memory) applies to the CURRENT device only: remember it per call site AND
+// per device, so that a process that drives a second GPU does not launch with the default limit there.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first()
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;      // unknown device: just set the attribute again
+        if (done[dev]) return false;
+        done[dev] = true;
+        return true;
+    }
+};
+
 constexpr int kNumSMs = 148;  // B200 (compile-time grid constants of the tensor-core kernels)
 int num_sms();                // multiProcessorCount of the current device, queried once per device
 

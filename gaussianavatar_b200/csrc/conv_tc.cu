@@ -221,10 +221,9 @@ __global__ void __launch_bounds__(256) round_tf32_kernel(const float *__restrict
 template <int MODE>
 int launch_mode(const ConvParams &p, int grid, const char *name, cudaStream_t st)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         GA_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvSmem) + 1024));
-        attr_set = true;
     }
     {
         ProfScope _ps(name, st);

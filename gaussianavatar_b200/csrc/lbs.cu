@@ -231,11 +231,10 @@ extern "C" int ga_lbs_forward(int32_t N, int32_t B, float scale_mul, int64_t dec
     GA_REQUIRE(N >= 0 && B >= 1 && B <= kMaxFrames, "bad LBS dims N=%d B=%d (B <= %d)", N, B, kMaxFrames);
     if (N == 0) return GA_OK;
     GA_REQUIRE(dec_out && valid_index && query_points && query_lbs && cano2live && means3D && scales3 && colors, "NULL pointer argument");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
         GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
-        attr_set = true;
     }
     { ProfScope _ps("lbs_kernel<fwd>", static_cast<cudaStream_t>(stream_)); launch_k(lbs_kernel<false>, launch_cfg(N), kTileN, sizeof(LbsSmem), static_cast<cudaStream_t>(stream_), 
         N, B, scale_mul, (long long)dec_frame_stride, dec_out, valid_index, query_points, query_lbs, cano2live, means3D, scales3, colors, nullptr, nullptr,
@@ -256,10 +255,9 @@ extern "C" int ga_lbs_backward(int32_t N, int32_t B, int32_t num_pixels, float s
     GA_CHECK_CUDA(cudaMemsetAsync(d_cano2live, 0, sizeof(float) * kJ * 12 * (size_t)B, stream));
     if (N == 0) return GA_OK;
     GA_REQUIRE(dec_out && valid_index && query_points && query_lbs && cano2live && d_means3D && d_scales3 && d_colors, "NULL pointer argument");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         GA_CHECK_CUDA(cudaFuncSetAttribute(lbs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LbsSmem)));
-        attr_set = true;
     }
     { ProfScope _ps("lbs_kernel<bwd>", stream); launch_k(lbs_kernel<true>, launch_cfg(N), kTileN, sizeof(LbsSmem), stream, N, B, scale_mul, (long long)dec_frame_stride, dec_out, valid_index, query_points,
                                                                         query_lbs, cano2live, nullptr, nullptr, nullptr,

@@ -278,10 +278,9 @@ int launch_tc_fwd(const float *X, int ldx, int K, const float *a, const float *b
     GA_REQUIRE(K % 8 == 0 && K >= 8 && K <= 128, "tcgen05 layer: K=%d must be a multiple of 8 in [8,128]", K);
     GA_REQUIRE(ldx % 4 == 0 && ldw % 4 == 0 && ldy % 4 == 0, "tcgen05 layer: leading dimensions must be multiples of 4");
     TcFwdParams p{X, ldx, K, a, b, W, ldw, bias, Y, ldy, accumulate, sum, sumsq, M};
-    static bool attr_t_set = false;
-    if (!attr_t_set) {
+    static PerDeviceOnce attr_t_set;
+    if (attr_t_set.first()) {
         GA_CHECK_CUDA(cudaFuncSetAttribute(tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcFwdTSmem) + 1024));
-        attr_t_set = true;
     }
     const int tiles = cdiv(M, kTPx);
     const int grid = tiles < kNumSMs ? tiles : kNumSMs;
@@ -792,10 +791,9 @@ int launch_tc_bwd(const float *dZ, const float *Y, int ldg, const float *ga, con
     GA_REQUIRE(kin % 4 == 0 && kin >= 4 && kin <= 128 && (!x_raw || mode == 1 || mode == 2), "tcgen05 backward: bad kin / mode");
     GA_REQUIRE(ldg % 4 == 0 && ldp % 4 == 0 && ldw % 4 == 0 && ldo % 4 == 0, "tcgen05 backward: leading dimensions must be multiples of 4");
     GA_REQUIRE(lddw % 4 == 0 && (reinterpret_cast<uintptr_t>(dW) & 15) == 0, "tcgen05 backward: dW must be 16-byte aligned with lddw a multiple of 4");
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         GA_CHECK_CUDA(cudaFuncSetAttribute(tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcBwdSmem) + 1024));
-        attr_set = true;
     }
     TcBwdParams p{dZ, Y, ldg, ga, m1, m2, mu, rstd, Yprev, ldp, pa, pb, pmu, prstd, W, ldw, dW, lddw, dZprev, ldo, mode, s1, s2, M, kin, x_raw};
     const int tiles = cdiv(M, kPx);

@@ -1204,11 +1204,10 @@ int launch_preprocess(const Dims &d, const CamSrc &cam, const FwdArgs &a, long l
 int launch_binning_and_render(const Dims &d, const FwdArgs &a, long long capacity, const GeomViews &g, const ImgViews &iv, const BinViews &bv,
                               float *out_color, cudaStream_t stream)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_set;
+    if (attr_set.first()) {
         GA_CHECK_CUDA(cudaFuncSetAttribute(tile_sort_kernel<kSortThreads, kSortMax, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSortMax * (int)sizeof(uint64_t)));
-        attr_set = true;
     }
     const int BT = d.B * d.T;
     if (d.P > 0) {
